@@ -1,0 +1,138 @@
+/*
+ * semdiff_b200 -- C-ABI of the B200-native global semantic-fidelity scorer ("CLIP-LPIPS regressor").
+ *
+ * The reference has no FFI: its scorer is a torch.nn.Module
+ * (/root/reference/models/global_eval_models.py:308-429 CLIP_lpips_stages_cnn,
+ *  :682-812 CLIP_lpips_stages_cnn_clsbckb).  This header is the boundary a maintainer binds to
+ * replace that module's forward(): plain pointers and sizes, no torch types.  Every pointer named
+ * "device" is CUDA device memory owned by the caller (PyTorch's caching allocator in the shipped
+ * host code); the library allocates nothing on the device.  Every entry point returns 0 on success
+ * and a negative code on failure, with a message available from semdiff_last_error().
+ * Launches are asynchronous on the given stream.  A plan is not thread-safe.
+ *
+ * Layouts: images in  = fp32 NCHW [n,3,H,W]           (what forward(a, b) receives, :341 / :717)
+ *          activations = NHWC, element type per `precision`, GT images first then SR images
+ *          conv weights = [Cout][KH][KW][Cin] (K-major rows), BatchNorm already folded
+ *          scores out  = fp32 [n]                      (what forward returns, :397 / :773)
+ */
+#ifndef SEMDIFF_B200_H_
+#define SEMDIFF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* semdiff_stream_t; /* == cudaStream_t */
+
+enum { SEMDIFF_OK = 0, SEMDIFF_ERR_ARG = -1, SEMDIFF_ERR_CUDA = -2, SEMDIFF_ERR_UNSUPPORTED = -3 };
+
+/* storage/compute type of the trunk.  Accumulation is always fp32. */
+enum { SEMDIFF_BF16 = 0, SEMDIFF_FP16 = 1, SEMDIFF_FP32 = 2 };
+
+/* conv implementation selector for semdiff_conv2d (the plan picks AUTO) */
+enum {
+  SEMDIFF_CONV_AUTO = 0,
+  SEMDIFF_CONV_SIMT = 1,      /* CUDA-core implicit GEMM, any precision (the only fp32 path) */
+  SEMDIFF_CONV_TC_GATHER = 2, /* tcgen05 + cp.async software im2col (any k/stride/pad, Cin % 8 == 0) */
+  SEMDIFF_CONV_TC_TMA = 3     /* tcgen05 + TMA tiled loads (1x1 stride 1) */
+};
+
+/* One step of the trunk program.  Buffers are logical ids in [0, n_bufs); buffer 0 is the packed
+ * input image batch.  The program is what /root/reference/models/global_eval_models.py:364,371
+ * (self.clip(a), self.clip(b)) executes inside timm, with BatchNorm folded. */
+enum { SEMDIFF_OP_CONV = 0, SEMDIFF_OP_MAXPOOL3S2 = 1, SEMDIFF_OP_AVGPOOL = 2, SEMDIFF_OP_TAP = 3 };
+
+typedef struct semdiff_op {
+  int32_t kind;      /* SEMDIFF_OP_* */
+  int32_t src;       /* input buffer id */
+  int32_t dst;       /* output buffer id (unused for TAP) */
+  int32_t res;       /* residual buffer id added before the activation, or -1 */
+  int32_t cin;       /* input channels as stored (multiple of 8; the image is padded 3 -> 8) */
+  int32_t cout;      /* output channels (conv) */
+  int32_t kh, kw;    /* kernel size (conv); pooling window for AVGPOOL (kh == kw == stride) */
+  int32_t stride;
+  int32_t pad;
+  int32_t relu;      /* apply ReLU in the epilogue */
+  int32_t tap;       /* for TAP: index j of w_layers[j] (:336) this activation feeds */
+  const void* weight; /* device, [cout][kh][kw][cin] in the plan's precision */
+  const float* bias;  /* device, [cout] fp32 (folded BN shift) */
+} semdiff_op;
+
+typedef struct semdiff_plan semdiff_plan;
+
+/* Build an execution plan for a trunk program.  Copies the op list (not the weights). */
+int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision,
+                        semdiff_plan** out_plan);
+int semdiff_plan_destroy(semdiff_plan* plan);
+/* Force the conv implementation of every conv op (SEMDIFF_CONV_*; AUTO = best supported). Testing aid. */
+int semdiff_plan_set_conv_impl(semdiff_plan* plan, int32_t impl);
+
+/* Bytes of device workspace semdiff_score needs for `microbatch_pairs` pairs of HxW images. */
+int64_t semdiff_workspace_bytes(const semdiff_plan* plan, int32_t microbatch_pairs, int32_t H, int32_t W);
+
+/* forward(a, b) -> score, :341-397 / :717-773.
+ *   gt, sr        device fp32 NCHW [n_pairs,3,H,W]
+ *   head_w        device fp32, w_layers[j].weight concatenated in tap order (sum_j C_j floats)
+ *   head_b        device fp32 [n_taps], w_layers[j].bias
+ *   out_scores    device fp32 [n_pairs]   = relu(mean_j(b_j + mean_hw sum_c w_j[c] (A-B)^2))
+ *   out_pre_relu  device fp32 [n_pairs] or NULL (same value before the final ReLU)
+ *   out_chan_mean device fp32 [n_pairs, sum_j C_j] or NULL: per-channel spatial means of (A-B)^2
+ *                 (d score / d w_j[c] * n_taps; lets the caller train w_layers, :55-69 of the sweep script)
+ * Pairs are processed in micro-batches of `microbatch_pairs` so that activations stay L2-resident. */
+int semdiff_score(semdiff_plan* plan, const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W,
+                  int32_t microbatch_pairs, const float* head_w, const float* head_b, int32_t normalize,
+                  void* workspace, int64_t workspace_bytes, float* out_scores, float* out_pre_relu,
+                  float* out_chan_mean, semdiff_stream_t stream);
+
+/* Profiling: when enabled, semdiff_score brackets every op with CUDA events on `stream`. */
+int semdiff_plan_set_profiling(semdiff_plan* plan, int32_t enable);
+/* Per-op accumulated milliseconds and launch counts since the last reset (arrays of n_ops + 3:
+ * the three extra slots are pack, distance (all taps), head). Synchronises the recorded events. */
+int semdiff_plan_get_profile(semdiff_plan* plan, float* out_ms, int32_t* out_launches, int32_t n, int32_t reset);
+/* Number of kernels launched by the last semdiff_score call on this plan. */
+int64_t semdiff_plan_last_launches(const semdiff_plan* plan);
+
+/* ---- single kernels (unit tests call these; the plan calls the same launchers) ------------- */
+
+/* fp32 NCHW [n,3,H,W] x2 -> NHWC [2n,H,W,8] (channels 3..7 zero), GT images first */
+int semdiff_pack_nhwc(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
+                      int32_t precision, semdiff_stream_t stream);
+
+/* out = act(conv(in, weight) + bias (+ residual)); NHWC; impl = SEMDIFF_CONV_* */
+int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out,
+                   int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw,
+                   int32_t stride, int32_t pad, int32_t relu, int32_t precision, int32_t impl,
+                   semdiff_stream_t stream);
+
+int semdiff_maxpool3x3s2(const void* in, void* out, int32_t n_img, int32_t H, int32_t W, int32_t c,
+                         int32_t precision, semdiff_stream_t stream);
+int semdiff_avgpool(const void* in, void* out, int32_t n_img, int32_t H, int32_t W, int32_t c, int32_t window,
+                    int32_t precision, semdiff_stream_t stream);
+
+/* Fused per-layer distance (:379-384 / :755-760): act = NHWC [2*n_pairs, HW, C] with GT image i at
+ * index i and SR image i at index n_pairs + i.  Writes partial[pair * SEMDIFF_MAX_PARTS + part] =
+ * sum over the part's elements of w[c] * (a-b)^2 (fixed order, no atomics); n_parts via
+ * semdiff_distance_parts().  chan_mean (nullable): [n_pairs, chan_stride] slice for this layer. */
+#define SEMDIFF_MAX_PARTS 64
+int32_t semdiff_distance_parts(int32_t hw, int32_t c);
+int semdiff_layer_distance(const void* act, int32_t n_pairs, int32_t hw, int32_t c, const float* w,
+                           int32_t normalize, float* partial, float* chan_mean, int32_t chan_stride,
+                           int32_t precision, semdiff_stream_t stream);
+
+/* Head (:385-395 / :761-771): score[p] = relu(mean_j(bias[j] + sum_parts partial_j[p] / hw_j)).
+ * partials: device [n_taps][n_pairs][SEMDIFF_MAX_PARTS]; n_parts/hw: host arrays [n_taps]. */
+int semdiff_head(const float* partials, int32_t n_taps, int32_t n_pairs, const int32_t* n_parts,
+                 const int32_t* hw, const float* head_b, float* out_scores, float* out_pre_relu,
+                 semdiff_stream_t stream);
+
+const char* semdiff_last_error(void);
+/* "semdiff_b200 <version> sm_100a" */
+const char* semdiff_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEMDIFF_B200_H_ */

@@ -1,0 +1,172 @@
+// Bandwidth-bound helpers of the trunk: image packing, max/avg pooling.  NHWC, 128-bit accesses.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace semdiff {
+
+// fp32 NCHW [n,3,H,W] (gt, sr) -> NHWC [2n,H,W,8], channels 3..7 = 0.  One thread per pixel: the three
+// plane reads are coalesced across the warp, the write is one 16 B (32 B for fp32) vector per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ gt, const float* __restrict__ sr,
+                                                   int n_pairs, int hw, T* __restrict__ out) {
+  const int64_t total = (int64_t)2 * n_pairs * hw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int img = (int)(i / hw);
+    const int pix = (int)(i - (int64_t)img * hw);
+    const float* src = (img < n_pairs ? gt + (int64_t)img * 3 * hw : sr + (int64_t)(img - n_pairs) * 3 * hw) + pix;
+    float f[8] = {__ldg(src), __ldg(src + hw), __ldg(src + 2 * hw), 0.f, 0.f, 0.f, 0.f, 0.f};
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(out + i * 8) = pack8<T>(f);
+    } else {
+      float4* o = reinterpret_cast<float4*>(out + i * 8);
+      o[0] = make_float4(f[0], f[1], f[2], 0.f);
+      o[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
+template <typename T> struct Vec8 {
+  static __device__ __forceinline__ void load(const T* p, float (&f)[8]) {
+    if constexpr (sizeof(T) == 2) {
+      uint4 q = *reinterpret_cast<const uint4*>(p);
+      unpack8<T>(q, f);
+    } else {
+      float4 a = reinterpret_cast<const float4*>(p)[0], b = reinterpret_cast<const float4*>(p)[1];
+      f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+  }
+  static __device__ __forceinline__ void store(T* p, const float (&f)[8]) {
+    if constexpr (sizeof(T) == 2) {
+      *reinterpret_cast<uint4*>(p) = pack8<T>(f);
+    } else {
+      reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+      reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+    }
+  }
+};
+
+// 3x3 stride-2 pad-1 max pool (torch MaxPool2d semantics: padding never wins)
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int H,
+                                                      int W, int C, int OH, int OW) {
+  const int cv = C / 8;
+  const int64_t total = (int64_t)n_img * OH * OW * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    int64_t p = i / cv;
+    const int ow = (int)(p % OW); p /= OW;
+    const int oh = (int)(p % OH);
+    const int n = (int)(p / OH);
+    float m[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        float f[8];
+        Vec8<T>::load(in + (((int64_t)n * H + ih) * W + iw) * C + c8 * 8, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+      }
+    }
+    Vec8<T>::store(out + i * 8, m);
+  }
+}
+
+// window x window average pool, stride = window (CLIP anti-aliased strides); trailing rows/cols are dropped
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int H,
+                                                      int W, int C, int win) {
+  const int cv = C / 8, OH = H / win, OW = W / win;
+  const int64_t total = (int64_t)n_img * OH * OW * cv;
+  const float inv = 1.f / (float)(win * win);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    int64_t p = i / cv;
+    const int ow = (int)(p % OW); p /= OW;
+    const int oh = (int)(p % OH);
+    const int n = (int)(p / OH);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < win; ++r)
+      for (int s = 0; s < win; ++s) {
+        float f[8];
+        Vec8<T>::load(in + (((int64_t)n * H + oh * win + r) * W + ow * win + s) * C + c8 * 8, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += f[k];
+      }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] *= inv;
+    Vec8<T>::store(out + i * 8, a);
+  }
+}
+
+static int grid_for(int64_t total, int block) {
+  int64_t g = (total + block - 1) / block;
+  const int64_t cap = 148 * 16;  // a few waves of 256-thread CTAs over 148 SMs; grid-stride covers the rest
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+template <typename T>
+static int pack_t(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, cudaStream_t st) {
+  const int64_t total = (int64_t)2 * n_pairs * H * W;
+  pack_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, H * W, (T*)out);
+  SEMDIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int precision, cudaStream_t st) {
+  if (n_pairs <= 0 || H <= 0 || W <= 0) { set_error("pack: bad shape"); return SEMDIFF_ERR_ARG; }
+  switch (precision) {
+    case SEMDIFF_BF16: return pack_t<__nv_bfloat16>(gt, sr, n_pairs, H, W, out, st);
+    case SEMDIFF_FP16: return pack_t<__half>(gt, sr, n_pairs, H, W, out, st);
+    case SEMDIFF_FP32: return pack_t<float>(gt, sr, n_pairs, H, W, out, st);
+  }
+  set_error("pack: bad precision %d", precision);
+  return SEMDIFF_ERR_ARG;
+}
+
+template <typename T>
+static int maxpool_t(const void* in, void* out, int n, int H, int W, int C, cudaStream_t st) {
+  const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)n * OH * OW * (C / 8);
+  maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)in, (T*)out, n, H, W, C, OH, OW);
+  SEMDIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_maxpool3x3s2(const void* in, void* out, int n, int H, int W, int C, int precision, cudaStream_t st) {
+  if (C % 8 != 0 || n <= 0) { set_error("maxpool: C %% 8 != 0 or empty"); return SEMDIFF_ERR_ARG; }
+  switch (precision) {
+    case SEMDIFF_BF16: return maxpool_t<__nv_bfloat16>(in, out, n, H, W, C, st);
+    case SEMDIFF_FP16: return maxpool_t<__half>(in, out, n, H, W, C, st);
+    case SEMDIFF_FP32: return maxpool_t<float>(in, out, n, H, W, C, st);
+  }
+  set_error("maxpool: bad precision %d", precision);
+  return SEMDIFF_ERR_ARG;
+}
+
+template <typename T>
+static int avgpool_t(const void* in, void* out, int n, int H, int W, int C, int win, cudaStream_t st) {
+  const int64_t total = (int64_t)n * (H / win) * (W / win) * (C / 8);
+  avgpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)in, (T*)out, n, H, W, C, win);
+  SEMDIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int win, int precision, cudaStream_t st) {
+  if (C % 8 != 0 || win < 1 || H < win || W < win || n <= 0) {  // floor semantics like torch AvgPool2d
+    set_error("avgpool: need C %% 8 == 0 and H, W >= window");
+    return SEMDIFF_ERR_ARG;
+  }
+  switch (precision) {
+    case SEMDIFF_BF16: return avgpool_t<__nv_bfloat16>(in, out, n, H, W, C, win, st);
+    case SEMDIFF_FP16: return avgpool_t<__half>(in, out, n, H, W, C, win, st);
+    case SEMDIFF_FP32: return avgpool_t<float>(in, out, n, H, W, C, win, st);
+  }
+  set_error("avgpool: bad precision %d", precision);
+  return SEMDIFF_ERR_ARG;
+}
+
+}  // namespace semdiff

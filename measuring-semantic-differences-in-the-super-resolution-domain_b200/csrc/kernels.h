@@ -1,0 +1,47 @@
+// Internal launcher declarations shared by the translation units of libsemdiff_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "semdiff_b200.h"
+
+namespace semdiff {
+
+struct ConvShape {
+  int n_img, H, W, cin, cout, kh, kw, stride, pad, relu;
+  int OH() const { return (H + 2 * pad - kh) / stride + 1; }
+  int OW() const { return (W + 2 * pad - kw) / stride + 1; }
+  int64_t M() const { return (int64_t)n_img * OH() * OW(); }
+  int K() const { return kh * kw * cin; }
+};
+
+inline size_t elem_bytes(int precision) { return precision == SEMDIFF_FP32 ? 4 : 2; }
+
+// each returns 0 / negative error code; all asynchronous on `stream`
+int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int precision,
+                cudaStream_t stream);
+int launch_maxpool3x3s2(const void* in, void* out, int n_img, int H, int W, int c, int precision, cudaStream_t stream);
+int launch_avgpool(const void* in, void* out, int n_img, int H, int W, int c, int window, int precision,
+                   cudaStream_t stream);
+int launch_conv_simt(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
+                     int precision, cudaStream_t stream);
+// tcgen05 path; use_tma selects the TMA-tiled A producer (1x1 stride 1 only) over the cp.async gather
+int launch_conv_tc(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
+                   int precision, bool use_tma, cudaStream_t stream);
+bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma);
+// prepared launch (TMA descriptors encoded once, reused while pointers and shapes stay the same)
+struct alignas(64) ConvTcLaunch {
+  unsigned char params[512];
+  int block_n, use_tma, precision;
+};
+int conv_tc_prepare(ConvTcLaunch* L, const void* in, const void* w, const float* bias, const void* res, void* out,
+                    const ConvShape& s, int precision, bool use_tma);
+int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream);
+
+int distance_parts(int hw, int c);
+int launch_distance(const void* act, int n_pairs, int hw, int c, const float* w, int normalize, float* partial,
+                    float* chan_mean, int chan_stride, int precision, cudaStream_t stream);
+int launch_head(const float* partials, int n_taps, int n_pairs, const int* n_parts, const int* hw, const float* head_b,
+                float* out_scores, float* out_pre_relu, cudaStream_t stream);
+
+}  // namespace semdiff

@@ -1,0 +1,385 @@
+// Host side of libsemdiff_b200.so: the trunk "program" executor (plan) and the C-ABI (include/semdiff_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <tuple>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace semdiff {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct BufShape { int h = 0, w = 0, c = 0; };
+
+// everything that depends on (workspace address, images in the micro-batch, H, W)
+struct ShapePlan {
+  std::vector<BufShape> op_src, op_dst;        // per op
+  std::vector<int64_t> buf_offset;             // per buffer, bytes from the workspace base
+  std::vector<ConvTcLaunch> tc;                // per op (valid where impl is a tcgen05 one)
+  std::vector<int> impl;                       // per op: SEMDIFF_CONV_*
+  int64_t partial_offset = 0;
+  int64_t total_bytes = 0;
+  bool prepared = false;
+  void* prepared_ws = nullptr;
+};
+
+}  // namespace semdiff
+
+using namespace semdiff;
+
+struct semdiff_plan {
+  std::vector<semdiff_op> ops;
+  int n_bufs = 0, precision = 0, n_taps = 0, conv_impl = SEMDIFF_CONV_AUTO;
+  std::vector<int> tap_c, tap_off;  // channels and head_w offset per tap
+  int chan_total = 0;
+  std::map<std::tuple<int, int, int>, ShapePlan> shapes;  // key: (pairs in micro-batch, H, W)
+  bool profiling = false;
+  struct Ev { int slot; cudaEvent_t a, b; };
+  std::vector<Ev> events;
+  std::vector<double> prof_ms;
+  std::vector<int> prof_launches;
+  int64_t last_launches = 0;
+};
+
+namespace semdiff {
+
+static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePlan* S) {
+  const int n_ops = (int)P->ops.size();
+  std::vector<BufShape> cur(P->n_bufs);
+  std::vector<int64_t> buf_elems(P->n_bufs, 0);
+  const int64_t n_img = 2 * (int64_t)pairs;
+  cur[0] = BufShape{H, W, 8};
+  buf_elems[0] = n_img * H * W * 8;
+  S->op_src.assign(n_ops, BufShape());
+  S->op_dst.assign(n_ops, BufShape());
+  for (int i = 0; i < n_ops; ++i) {
+    const semdiff_op& op = P->ops[i];
+    if (op.src < 0 || op.src >= P->n_bufs) { set_error("op %d: bad src buffer %d", i, op.src); return SEMDIFF_ERR_ARG; }
+    const BufShape in = cur[op.src];
+    if (in.c == 0) { set_error("op %d reads buffer %d before it is written", i, op.src); return SEMDIFF_ERR_ARG; }
+    S->op_src[i] = in;
+    BufShape out;
+    switch (op.kind) {
+      case SEMDIFF_OP_CONV:
+        if (in.c != op.cin) { set_error("op %d: cin %d != buffer channels %d", i, op.cin, in.c); return SEMDIFF_ERR_ARG; }
+        out = BufShape{(in.h + 2 * op.pad - op.kh) / op.stride + 1, (in.w + 2 * op.pad - op.kw) / op.stride + 1, op.cout};
+        if (op.res >= 0) {
+          if (op.res >= P->n_bufs) { set_error("op %d: bad residual buffer", i); return SEMDIFF_ERR_ARG; }
+          const BufShape r = cur[op.res];
+          if (r.h != out.h || r.w != out.w || r.c != out.c) {
+            set_error("op %d: residual shape %dx%dx%d != output %dx%dx%d", i, r.h, r.w, r.c, out.h, out.w, out.c);
+            return SEMDIFF_ERR_ARG;
+          }
+        }
+        break;
+      case SEMDIFF_OP_MAXPOOL3S2: out = BufShape{(in.h - 1) / 2 + 1, (in.w - 1) / 2 + 1, in.c}; break;
+      case SEMDIFF_OP_AVGPOOL: out = BufShape{in.h / op.stride, in.w / op.stride, in.c}; break;
+      case SEMDIFF_OP_TAP: continue;
+      default: set_error("op %d: unknown kind %d", i, op.kind); return SEMDIFF_ERR_ARG;
+    }
+    if (out.h <= 0 || out.w <= 0) { set_error("op %d: empty output (input %dx%d too small)", i, in.h, in.w); return SEMDIFF_ERR_ARG; }
+    if (op.dst <= 0 || op.dst >= P->n_bufs || op.dst == op.src || op.dst == op.res) {
+      set_error("op %d: bad dst buffer %d", i, op.dst);
+      return SEMDIFF_ERR_ARG;
+    }
+    S->op_dst[i] = out;
+    cur[op.dst] = out;
+    const int64_t e = n_img * out.h * out.w * out.c;
+    if (e > buf_elems[op.dst]) buf_elems[op.dst] = e;
+  }
+  S->buf_offset.assign(P->n_bufs, 0);
+  int64_t off = 0;
+  const int64_t eb = (int64_t)elem_bytes(P->precision);
+  for (int b = 0; b < P->n_bufs; ++b) {
+    S->buf_offset[b] = off;
+    off += (buf_elems[b] * eb + 1023) / 1024 * 1024;
+  }
+  S->partial_offset = off;
+  off += (int64_t)(P->n_taps > 0 ? P->n_taps : 1) * pairs * SEMDIFF_MAX_PARTS * 4;
+  S->total_bytes = (off + 1023) / 1024 * 1024;
+  return 0;
+}
+
+static int choose_impl(const semdiff_plan* P, const ConvShape& cs) {
+  if (P->precision == SEMDIFF_FP32 || P->conv_impl == SEMDIFF_CONV_SIMT) return SEMDIFF_CONV_SIMT;
+  if (P->conv_impl != SEMDIFF_CONV_TC_GATHER && conv_tc_supported(cs, P->precision, true)) return SEMDIFF_CONV_TC_TMA;
+  if (conv_tc_supported(cs, P->precision, false)) return SEMDIFF_CONV_TC_GATHER;
+  return SEMDIFF_CONV_SIMT;
+}
+
+static ConvShape conv_shape(const semdiff_op& op, const BufShape& in, int n_img) {
+  ConvShape cs;
+  cs.n_img = n_img; cs.H = in.h; cs.W = in.w; cs.cin = op.cin; cs.cout = op.cout; cs.kh = op.kh; cs.kw = op.kw;
+  cs.stride = op.stride; cs.pad = op.pad; cs.relu = op.relu;
+  return cs;
+}
+
+static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
+  const int n_ops = (int)P->ops.size();
+  S->tc.resize(n_ops);
+  S->impl.assign(n_ops, 0);
+  for (int i = 0; i < n_ops; ++i) {
+    const semdiff_op& op = P->ops[i];
+    if (op.kind != SEMDIFF_OP_CONV) continue;
+    const ConvShape cs = conv_shape(op, S->op_src[i], 2 * pairs);
+    const int impl = choose_impl(P, cs);
+    S->impl[i] = impl;
+    if (impl == SEMDIFF_CONV_TC_TMA || impl == SEMDIFF_CONV_TC_GATHER) {
+      int rc = conv_tc_prepare(&S->tc[i], ws + S->buf_offset[op.src], op.weight, op.bias,
+                               op.res >= 0 ? ws + S->buf_offset[op.res] : nullptr, ws + S->buf_offset[op.dst], cs,
+                               P->precision, impl == SEMDIFF_CONV_TC_TMA);
+      if (rc != 0) return rc;
+    }
+  }
+  S->prepared = true;
+  S->prepared_ws = ws;
+  return 0;
+}
+
+struct ProfScope {
+  semdiff_plan* P; int slot; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(semdiff_plan* p, int s, cudaStream_t stream) : P(p), slot(s), st(stream) {
+    if (P->profiling) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (P->profiling) { cudaEventRecord(b, st); P->events.push_back({slot, a, b}); }
+  }
+};
+
+}  // namespace semdiff
+
+extern "C" {
+#pragma GCC visibility push(default)
+
+const char* semdiff_last_error(void) { return g_err; }
+const char* semdiff_version(void) { return "semdiff_b200 0.1 sm_100a"; }
+
+int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision, semdiff_plan** out) {
+  if (ops == nullptr || out == nullptr || n_ops <= 0 || n_bufs < 2) { set_error("plan_create: bad arguments"); return SEMDIFF_ERR_ARG; }
+  if (precision < SEMDIFF_BF16 || precision > SEMDIFF_FP32) { set_error("plan_create: bad precision %d", precision); return SEMDIFF_ERR_ARG; }
+  semdiff_plan* P = new semdiff_plan();
+  P->ops.assign(ops, ops + n_ops);
+  P->n_bufs = n_bufs;
+  P->precision = precision;
+  for (const semdiff_op& op : P->ops)
+    if (op.kind == SEMDIFF_OP_TAP && op.tap + 1 > P->n_taps) P->n_taps = op.tap + 1;
+  if (P->n_taps < 1 || P->n_taps > 16) { delete P; set_error("plan_create: need 1..16 TAP ops, got %d", P->n_taps); return SEMDIFF_ERR_ARG; }
+  // tap channel counts come from a dry shape inference at a nominal size
+  ShapePlan S;
+  int rc = infer_shapes(P, 1, 224, 224, &S);
+  if (rc != 0) { delete P; return rc; }
+  P->tap_c.assign(P->n_taps, 0);
+  for (size_t i = 0; i < P->ops.size(); ++i)
+    if (P->ops[i].kind == SEMDIFF_OP_TAP) P->tap_c[P->ops[i].tap] = S.op_src[i].c;
+  P->tap_off.assign(P->n_taps, 0);
+  int off = 0;
+  for (int j = 0; j < P->n_taps; ++j) {
+    if (P->tap_c[j] == 0) { delete P; set_error("plan_create: tap %d missing", j); return SEMDIFF_ERR_ARG; }
+    P->tap_off[j] = off;
+    off += P->tap_c[j];
+  }
+  P->chan_total = off;
+  P->prof_ms.assign(n_ops + 3, 0.0);
+  P->prof_launches.assign(n_ops + 3, 0);
+  *out = P;
+  return 0;
+}
+
+int semdiff_plan_destroy(semdiff_plan* P) {
+  if (P == nullptr) return 0;
+  for (auto& e : P->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  delete P;
+  return 0;
+}
+
+int semdiff_plan_set_conv_impl(semdiff_plan* P, int32_t impl) {
+  if (P == nullptr || impl < SEMDIFF_CONV_AUTO || impl > SEMDIFF_CONV_TC_TMA) { set_error("set_conv_impl: bad argument"); return SEMDIFF_ERR_ARG; }
+  P->conv_impl = impl;
+  P->shapes.clear();
+  return 0;
+}
+
+int64_t semdiff_workspace_bytes(const semdiff_plan* P, int32_t pairs, int32_t H, int32_t W) {
+  if (P == nullptr || pairs <= 0 || H <= 0 || W <= 0) { set_error("workspace_bytes: bad arguments"); return SEMDIFF_ERR_ARG; }
+  ShapePlan S;
+  int rc = infer_shapes(P, pairs, H, W, &S);
+  if (rc != 0) return rc;
+  return S.total_bytes;
+}
+
+int semdiff_plan_set_profiling(semdiff_plan* P, int32_t enable) {
+  if (P == nullptr) return SEMDIFF_ERR_ARG;
+  P->profiling = enable != 0;
+  return 0;
+}
+
+int semdiff_plan_get_profile(semdiff_plan* P, float* out_ms, int32_t* out_launches, int32_t n, int32_t reset) {
+  if (P == nullptr || n < (int)P->prof_ms.size()) { set_error("get_profile: need arrays of n_ops + 3"); return SEMDIFF_ERR_ARG; }
+  for (auto& e : P->events) {
+    SEMDIFF_CUDA_OK(cudaEventSynchronize(e.b));
+    float ms = 0.f;
+    SEMDIFF_CUDA_OK(cudaEventElapsedTime(&ms, e.a, e.b));
+    P->prof_ms[e.slot] += ms;
+    P->prof_launches[e.slot] += 1;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  P->events.clear();
+  for (size_t i = 0; i < P->prof_ms.size(); ++i) {
+    if (out_ms) out_ms[i] = (float)P->prof_ms[i];
+    if (out_launches) out_launches[i] = P->prof_launches[i];
+  }
+  if (reset) {
+    std::fill(P->prof_ms.begin(), P->prof_ms.end(), 0.0);
+    std::fill(P->prof_launches.begin(), P->prof_launches.end(), 0);
+  }
+  return 0;
+}
+
+int64_t semdiff_plan_last_launches(const semdiff_plan* P) { return P ? P->last_launches : -1; }
+
+int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W,
+                  int32_t mb, const float* head_w, const float* head_b, int32_t normalize, void* workspace,
+                  int64_t workspace_bytes, float* out_scores, float* out_pre_relu, float* out_chan_mean,
+                  semdiff_stream_t stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  if (P == nullptr || gt == nullptr || sr == nullptr || head_w == nullptr || head_b == nullptr || workspace == nullptr ||
+      out_scores == nullptr) { set_error("score: null argument"); return SEMDIFF_ERR_ARG; }
+  if (n_pairs < 0 || H <= 0 || W <= 0 || mb <= 0) { set_error("score: bad sizes"); return SEMDIFF_ERR_ARG; }
+  P->last_launches = 0;
+  if (n_pairs == 0) return 0;  // empty batch -> empty result, like the reference
+  if (mb > n_pairs) mb = n_pairs;
+  const int n_ops = (int)P->ops.size();
+  const int64_t img_elems = (int64_t)3 * H * W;
+  char* ws = reinterpret_cast<char*>(workspace);
+
+  for (int p0 = 0; p0 < n_pairs; p0 += mb) {
+    const int cur = n_pairs - p0 < mb ? n_pairs - p0 : mb;
+    ShapePlan& S = P->shapes[std::make_tuple(cur, H, W)];
+    if (S.total_bytes == 0) {
+      int rc = infer_shapes(P, cur, H, W, &S);
+      if (rc != 0) return rc;
+    }
+    if (S.total_bytes > workspace_bytes) {
+      set_error("score: workspace too small (%lld needed, %lld given)", (long long)S.total_bytes, (long long)workspace_bytes);
+      return SEMDIFF_ERR_ARG;
+    }
+    if (!S.prepared || S.prepared_ws != ws) {
+      int rc = prepare(P, &S, cur, ws);
+      if (rc != 0) return rc;
+    }
+    float* partials = reinterpret_cast<float*>(ws + S.partial_offset);
+    int tap_parts[16], tap_hw[16];
+    {
+      ProfScope ps(P, n_ops + 0, st);
+      int rc = launch_pack(gt + p0 * img_elems, sr + p0 * img_elems, cur, H, W, ws + S.buf_offset[0], P->precision, st);
+      if (rc != 0) return rc;
+      P->last_launches++;
+    }
+    for (int i = 0; i < n_ops; ++i) {
+      const semdiff_op& op = P->ops[i];
+      const BufShape in = S.op_src[i];
+      char* src = ws + S.buf_offset[op.src];
+      int rc = 0;
+      if (op.kind == SEMDIFF_OP_TAP) {
+        ProfScope ps(P, n_ops + 1, st);
+        const int j = op.tap, hw = in.h * in.w;
+        tap_parts[j] = distance_parts(hw, in.c);
+        tap_hw[j] = hw;
+        float* cm = out_chan_mean ? out_chan_mean + (int64_t)p0 * P->chan_total + P->tap_off[j] : nullptr;
+        rc = launch_distance(src, cur, hw, in.c, head_w + P->tap_off[j], normalize,
+                             partials + (int64_t)j * cur * SEMDIFF_MAX_PARTS, cm, P->chan_total, P->precision, st);
+        P->last_launches += cm ? 2 : 1;
+      } else {
+        ProfScope ps(P, i, st);
+        char* dst = ws + S.buf_offset[op.dst];
+        if (op.kind == SEMDIFF_OP_CONV) {
+          if (S.impl[i] == SEMDIFF_CONV_SIMT) {
+            rc = launch_conv_simt(src, op.weight, op.bias, op.res >= 0 ? ws + S.buf_offset[op.res] : nullptr, dst,
+                                  conv_shape(op, in, 2 * cur), P->precision, st);
+          } else {
+            rc = conv_tc_launch(&S.tc[i], st);
+          }
+        } else if (op.kind == SEMDIFF_OP_MAXPOOL3S2) {
+          rc = launch_maxpool3x3s2(src, dst, 2 * cur, in.h, in.w, in.c, P->precision, st);
+        } else {
+          rc = launch_avgpool(src, dst, 2 * cur, in.h, in.w, in.c, op.stride, P->precision, st);
+        }
+        P->last_launches++;
+      }
+      if (rc != 0) return rc;
+    }
+    {
+      ProfScope ps(P, n_ops + 2, st);
+      int rc = launch_head(partials, P->n_taps, cur, tap_parts, tap_hw, head_b, out_scores + p0,
+                           out_pre_relu ? out_pre_relu + p0 : nullptr, st);
+      if (rc != 0) return rc;
+      P->last_launches++;
+    }
+  }
+  return 0;
+}
+
+int semdiff_pack_nhwc(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
+                      int32_t precision, semdiff_stream_t st) {
+  return launch_pack(gt, sr, n_pairs, H, W, out, precision, reinterpret_cast<cudaStream_t>(st));
+}
+
+int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out, int32_t n_img,
+                   int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
+                   int32_t relu, int32_t precision, int32_t impl, semdiff_stream_t st_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(st_);
+  ConvShape cs;
+  cs.n_img = n_img; cs.H = H; cs.W = W; cs.cin = cin; cs.cout = cout; cs.kh = kh; cs.kw = kw; cs.stride = stride;
+  cs.pad = pad; cs.relu = relu;
+  if (n_img <= 0 || cs.OH() <= 0 || cs.OW() <= 0 || stride < 1) { set_error("conv2d: bad shape"); return SEMDIFF_ERR_ARG; }
+  if (impl == SEMDIFF_CONV_AUTO) {
+    semdiff_plan tmp;
+    tmp.precision = precision;
+    impl = choose_impl(&tmp, cs);
+  }
+  switch (impl) {
+    case SEMDIFF_CONV_SIMT: return launch_conv_simt(in, weight, bias, residual, out, cs, precision, st);
+    case SEMDIFF_CONV_TC_GATHER: return launch_conv_tc(in, weight, bias, residual, out, cs, precision, false, st);
+    case SEMDIFF_CONV_TC_TMA: return launch_conv_tc(in, weight, bias, residual, out, cs, precision, true, st);
+  }
+  set_error("conv2d: bad impl %d", impl);
+  return SEMDIFF_ERR_ARG;
+}
+
+int semdiff_maxpool3x3s2(const void* in, void* out, int32_t n, int32_t H, int32_t W, int32_t c, int32_t precision,
+                         semdiff_stream_t st) {
+  return launch_maxpool3x3s2(in, out, n, H, W, c, precision, reinterpret_cast<cudaStream_t>(st));
+}
+int semdiff_avgpool(const void* in, void* out, int32_t n, int32_t H, int32_t W, int32_t c, int32_t window,
+                    int32_t precision, semdiff_stream_t st) {
+  return launch_avgpool(in, out, n, H, W, c, window, precision, reinterpret_cast<cudaStream_t>(st));
+}
+
+int32_t semdiff_distance_parts(int32_t hw, int32_t c) { return distance_parts(hw, c); }
+
+int semdiff_layer_distance(const void* act, int32_t n_pairs, int32_t hw, int32_t c, const float* w, int32_t normalize,
+                           float* partial, float* chan_mean, int32_t chan_stride, int32_t precision, semdiff_stream_t st) {
+  return launch_distance(act, n_pairs, hw, c, w, normalize, partial, chan_mean, chan_stride, precision,
+                         reinterpret_cast<cudaStream_t>(st));
+}
+
+int semdiff_head(const float* partials, int32_t n_taps, int32_t n_pairs, const int32_t* n_parts, const int32_t* hw,
+                 const float* head_b, float* out_scores, float* out_pre_relu, semdiff_stream_t st) {
+  return launch_head(partials, n_taps, n_pairs, n_parts, hw, head_b, out_scores, out_pre_relu,
+                     reinterpret_cast<cudaStream_t>(st));
+}
+
+#pragma GCC visibility pop
+}  // extern "C"

@@ -1,0 +1,242 @@
+"""Drop-in B200 replacements for the reference's global semantic-fidelity scorers.
+
+    reference                                                     here
+    models/global_eval_models.py:308  CLIP_lpips_stages_cnn        CLIP_lpips_stages_cnn
+    models/global_eval_models.py:682  CLIP_lpips_stages_cnn_clsbckb CLIP_lpips_stages_cnn_clsbckb
+
+Same constructor `(clip_name, depth, device, enc_ft=False)`, same `forward(a, b) -> Tensor[N]`, same attributes
+(`clip`, `depth`, `enc_ft`, `wanted_layers`, `w_layers`, `final_relu`, `processor`), same `state_dict()` keys and
+`save_model` / `load_model` files, so the module drops into datasets/global_eval_torch_ds.py and the sweep script.
+Underneath, forward() is ONE call into libsemdiff_b200.so (include/semdiff_b200.h: semdiff_score): hand-written
+sm_100a kernels run both trunk passes (GT and SR batched through the same launches, BatchNorm folded, bias + ReLU +
+residual fused into the tcgen05 implicit-GEMM epilogue), the fused per-layer distance and the head.
+
+Deliberate differences from the reference (all documented in DESIGN.md):
+  * CUDA only.  There is no CPU or PyTorch fallback; a non-CUDA device raises.
+  * The trunk is inference-only: `enc_ft=True` raises, and `model.train()` does not put BatchNorm in training
+    mode (the reference's training loop does so by accident, CLIPLPIPS_REG_training_sweep_example.py:59).
+  * Keyword-only extras: `precision` ("bf16" default | "fp16" | "fp32"), `microbatch`, `normalize`
+    (LPIPS-style channel unit-normalisation; default False because the reference does not normalise, :379).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _lib, trunks
+from .processor import make_processor
+
+
+class _Plan:
+    """Device-resident folded weights + the native plan handle.  Rebuilt when trunk weights change."""
+
+    def __init__(self, clip: nn.Module, family: str, depth: int, precision: str, device: torch.device):
+        self.lib = _lib.load()
+        self.precision = _lib.PRECISIONS[precision]
+        dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[precision]
+        self.program = trunks.LOWER[family](clip, depth)
+        ops = self.program.ops
+        self._keep = []
+        arr = (_lib.SemdiffOp * len(ops))()
+        for i, op in enumerate(ops):
+            w_ptr = b_ptr = None
+            if op["kind"] == _lib.OP_CONV:
+                w = op["w"].to(dt).to(device).contiguous()
+                b = op["b"].to(torch.float32).to(device).contiguous()
+                self._keep += [w, b]
+                w_ptr, b_ptr = w.data_ptr(), b.data_ptr()
+            arr[i] = _lib.SemdiffOp(op["kind"], op["src"], op["dst"], op["res"], op["cin"], op["cout"], op["kh"],
+                                    op["kw"], op["stride"], op["pad"], op["relu"], op["tap"], w_ptr, b_ptr)
+        handle = C.c_void_p()
+        _lib.check(self.lib.semdiff_plan_create(arr, len(ops), self.program.n_bufs, self.precision, C.byref(handle)),
+                   "semdiff_plan_create")
+        self.handle = handle
+        self.n_ops = len(ops)
+        self.device = device
+        self._ws = None
+
+    def workspace(self, pairs: int, H: int, W: int) -> torch.Tensor:
+        need = _lib.check(self.lib.semdiff_workspace_bytes(self.handle, pairs, H, W), "semdiff_workspace_bytes")
+        if self._ws is None or self._ws.numel() < need:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._ws
+
+    def set_conv_impl(self, impl: int):
+        _lib.check(self.lib.semdiff_plan_set_conv_impl(self.handle, impl), "semdiff_plan_set_conv_impl")
+
+    def set_profiling(self, on: bool):
+        _lib.check(self.lib.semdiff_plan_set_profiling(self.handle, int(on)), "semdiff_plan_set_profiling")
+
+    def profile(self, reset: bool = True):
+        n = self.n_ops + 3
+        ms, cnt = (C.c_float * n)(), (C.c_int32 * n)()
+        _lib.check(self.lib.semdiff_plan_get_profile(self.handle, ms, cnt, n, int(reset)), "semdiff_plan_get_profile")
+        return list(ms), list(cnt)
+
+    def last_launches(self) -> int:
+        return int(self.lib.semdiff_plan_last_launches(self.handle))
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.semdiff_plan_destroy(self.handle)
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+class _ScoreFn(torch.autograd.Function):
+    """score = relu(mean_j(b_j + sum_c w_j[c] * m_j[c])), m_j[c] = spatial mean of (A-B)^2 (kernel output).
+    Gradients flow to w_layers only (the trunk is frozen, like the reference with enc_ft=False)."""
+
+    @staticmethod
+    def forward(ctx, module, a, b, head_w, head_b):
+        scores, pre, chan = module._run(a, b, head_w, head_b, want_grad=True)
+        ctx.save_for_backward(pre, chan)
+        ctx.n_taps = head_b.numel()
+        ctx.offsets = module._tap_offsets
+        return scores
+
+    @staticmethod
+    def backward(ctx, g):
+        pre, chan = ctx.saved_tensors
+        gate = (g * (pre > 0).to(g.dtype)) / ctx.n_taps          # [N]
+        grad_w = gate @ chan                                      # [sum C]
+        grad_b = gate.sum().expand(ctx.n_taps).clone()
+        return None, None, None, grad_w, grad_b
+
+
+class _B200Scorer(nn.Module):
+    _DEFAULT_TRUNK = None  # set by subclasses; only used for the tap-name pattern
+
+    def __init__(self, clip_name: str, depth: int, device: str, enc_ft: bool = False, *, precision: str = "bf16",
+                 microbatch: int | None = None, normalize: bool = False):
+        super().__init__()
+        if enc_ft:
+            raise NotImplementedError(
+                "enc_ft=True (fine-tuning the trunk through autograd) is not supported by the B200 scorer: the trunk "
+                "is an inference-only kernel program with folded BatchNorm")
+        if not (0 <= int(depth) <= 3):
+            raise ValueError("depth must be in 0..3 (w_layers = Conv2d(256 * 2**s, 1, 1) for s in range(3-depth, 4))")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError(f"device={device!r}: the B200 scorer has no CPU fallback; use the reference module on CPU")
+        _lib.load()  # fail loudly now if the CUDA library is missing
+        self.family = trunks.trunk_family(clip_name)
+        self.clip = trunks.create_trunk(clip_name)
+        self.enc_ft = enc_ft
+        self.clip.eval()
+        self.clip.to(dev)
+        self.depth = depth
+        self.wanted_layers = self._tap_names(depth)
+        print(self.wanted_layers)  # the reference prints this too (:328 / :702)
+        cfg = getattr(self.clip, "pretrained_cfg", None) or {}
+        self.processor = make_processor(dict(cfg))
+        self.w_layers = nn.ModuleList([nn.Conv2d(256 * (2 ** s), 1, kernel_size=1, stride=1) for s in range(3 - depth, 4)])
+        self.final_relu = nn.ReLU()
+        self.w_layers.to(dev)
+        self.precision, self.microbatch, self.normalize = precision, microbatch, normalize
+        self._device = dev
+        self._plan: _Plan | None = None
+        self._tap_offsets = []
+        off = 0
+        for m in self.w_layers:
+            self._tap_offsets.append(off)
+            off += m.in_channels
+
+    # ---- reference API -------------------------------------------------------------------
+    def forward(self, a, b):
+        if a.shape != b.shape or a.dim() != 4 or a.shape[1] != 3:
+            raise ValueError(f"expected two [N,3,H,W] tensors of the same shape, got {tuple(a.shape)} and {tuple(b.shape)}")
+        if a.device.type != "cuda" or b.device.type != "cuda":
+            raise RuntimeError("inputs must be CUDA tensors (no CPU fallback)")
+        head_w = torch.cat([m.weight.reshape(-1) for m in self.w_layers]).float()
+        head_b = torch.cat([m.bias.reshape(-1) for m in self.w_layers]).float()
+        if torch.is_grad_enabled() and (head_w.requires_grad or head_b.requires_grad):
+            return _ScoreFn.apply(self, a, b, head_w, head_b)
+        return self._run(a, b, head_w, head_b)[0]
+
+    def save_model(self, path: str):
+        torch.save(self.w_layers.state_dict(), path)  # enc_ft is always False here (:423)
+
+    def load_model(self, path: str):
+        self.w_layers.load_state_dict(torch.load(path, weights_only=True))  # (:429)
+
+    def init_weights(self):
+        """No-op, like the reference's (:807-812 looks for nn.Linear inside w_layers and never finds one)."""
+
+    # ---- nn.Module plumbing: keep the native plan in sync with the parameters --------------
+    def train(self, mode: bool = True):
+        super().train(mode)
+        self.clip.eval()  # folded BatchNorm: the trunk has no training mode
+        return self
+
+    def _apply(self, fn, *args, **kwargs):
+        self._plan = None
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._plan = None
+        return super().load_state_dict(*args, **kwargs)
+
+    def refresh(self):
+        """Re-fold the trunk after its parameters were modified in place."""
+        self._plan = None
+
+    # ---- native call -----------------------------------------------------------------------
+    def plan(self) -> _Plan:
+        if self._plan is None:
+            dev = next(self.w_layers.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("the module was moved off the GPU; the B200 scorer has no CPU fallback")
+            self._plan = _Plan(self.clip, self.family, self.depth, self.precision, dev)
+        return self._plan
+
+    def default_microbatch(self, H: int, W: int) -> int:
+        if self.microbatch:
+            return int(self.microbatch)
+        # keep ~4 live activation buffers of the widest layer (H/4 x W/4 x 256 x 2 images) inside ~1/2 of the L2
+        per_pair = 2 * (H // 4) * (W // 4) * 256 * (4 if self.precision == "fp32" else 2) * 4
+        return max(1, min(64, (64 << 20) // max(per_pair, 1)))
+
+    def _run(self, a, b, head_w, head_b, want_grad: bool = False):
+        plan = self.plan()
+        n, _, H, W = a.shape
+        a = a.detach().contiguous().float()
+        b = b.detach().contiguous().float()
+        hw_, hb_ = head_w.detach().contiguous(), head_b.detach().contiguous()
+        out = torch.empty(n, dtype=torch.float32, device=a.device)
+        if n == 0:
+            return out, out, None
+        mb = min(self.default_microbatch(H, W), n)
+        ws = plan.workspace(mb, H, W)
+        pre = torch.empty_like(out) if want_grad else None
+        chan = torch.empty(n, hw_.numel(), dtype=torch.float32, device=a.device) if want_grad else None
+        with torch.cuda.device(a.device):
+            rc = plan.lib.semdiff_score(plan.handle, a.data_ptr(), b.data_ptr(), n, H, W, mb, hw_.data_ptr(),
+                                        hb_.data_ptr(), int(self.normalize), ws.data_ptr(), ws.numel(),
+                                        out.data_ptr(), pre.data_ptr() if want_grad else None,
+                                        chan.data_ptr() if want_grad else None, _lib.stream_ptr())
+        _lib.check(rc, "semdiff_score")
+        return out, pre, chan
+
+
+class CLIP_lpips_stages_cnn(_B200Scorer):
+    """timm ByobNet `resnet50_clip.openai` trunk; taps stages.{s}.2.act (reference :308-429)."""
+
+    def _tap_names(self, depth):
+        if self.family != "resnet50_clip.openai":
+            raise ValueError("CLIP_lpips_stages_cnn hooks `stages.{s}.2.act`; use a resnet50_clip.* trunk (reference :327)")
+        return [f"stages.{s}.{2}.act" for s in range(3 - depth, 4)]
+
+
+class CLIP_lpips_stages_cnn_clsbckb(_B200Scorer):
+    """timm `resnet50` (ImageNet) trunk; taps layer{s}.2.act3 (reference :682-812)."""
+
+    def _tap_names(self, depth):
+        if self.family != "resnet50":
+            raise ValueError("CLIP_lpips_stages_cnn_clsbckb hooks `layer{s}.2.act3`; use a resnet50 trunk (reference :701)")
+        return [f"layer{s}.2.act3" for s in range(4 - depth, 5)]

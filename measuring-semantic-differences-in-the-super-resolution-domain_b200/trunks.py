@@ -1,0 +1,264 @@
+"""Trunk parameter containers and trunk -> kernel-program lowering.
+
+The reference gets its trunk from timm (`timm.create_model(clip_name, pretrained=True)`,
+/root/reference/models/global_eval_models.py:315 and :689).  Here the trunk never runs in PyTorch:
+`self.clip` only has to (a) own the parameters under timm's key names so that state_dict()/load_state_dict()
+round-trip with reference checkpoints and (b) be walkable by name so it can be lowered to the
+op list libsemdiff_b200.so executes (BatchNorm folded into the conv weights in fp64).
+
+If a real `timm` is installed, its model object is used as the container (pretrained weights);
+otherwise a structurally identical tree with a seeded random init is built (there is no network here).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+_NO_FWD = ("this trunk runs inside libsemdiff_b200.so (hand-written sm_100a kernels); the PyTorch module only "
+           "holds its parameters and there is no PyTorch/CPU fallback")
+
+
+class ParamTree(nn.Module):
+    """A named bag of sub-modules/parameters; calling it is an error by design."""
+
+    def forward(self, *args, **kwargs):
+        raise RuntimeError(_NO_FWD)
+
+
+def _seq(mods):
+    t = ParamTree()
+    for i, m in enumerate(mods):
+        t.add_module(str(i), m)
+    return t
+
+
+def _conv(cin, cout, k, stride=1):
+    return nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2, bias=False)
+
+
+# ---- ImageNet ResNet-50 (timm `resnet50`): keys conv1, bn1, layer{1..4}.{i}.{conv,bn}{1,2,3}, downsample.{0,1}, fc
+RESNET50_STAGES = ((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2))  # planes, blocks, stride of block 0
+
+
+def resnet50_tree() -> nn.Module:
+    root = ParamTree()
+    root.conv1, root.bn1, root.act1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU()
+    root.maxpool = nn.MaxPool2d(3, 2, 1)
+    cin = 64
+    for li, (planes, blocks, stride) in enumerate(RESNET50_STAGES, start=1):
+        blks = []
+        for b in range(blocks):
+            blk = ParamTree()
+            s = stride if b == 0 else 1
+            blk.conv1, blk.bn1, blk.act1 = _conv(cin, planes, 1), nn.BatchNorm2d(planes), nn.ReLU()
+            blk.conv2, blk.bn2, blk.act2 = _conv(planes, planes, 3, s), nn.BatchNorm2d(planes), nn.ReLU()
+            blk.conv3, blk.bn3, blk.act3 = _conv(planes, planes * 4, 1), nn.BatchNorm2d(planes * 4), nn.ReLU()
+            if b == 0:
+                blk.downsample = _seq([nn.Conv2d(cin, planes * 4, 1, s, bias=False), nn.BatchNorm2d(planes * 4)])
+            blks.append(blk)
+            cin = planes * 4
+        root.add_module(f"layer{li}", _seq(blks))
+    root.global_pool = nn.AdaptiveAvgPool2d(1)
+    root.fc = nn.Linear(2048, 1000)
+    root.pretrained_cfg = {"input_size": (3, 224, 224), "interpolation": "bicubic", "crop_pct": 0.95,
+                           "mean": (0.485, 0.456, 0.406), "std": (0.229, 0.224, 0.225)}
+    return root
+
+
+# ---- CLIP ResNet-50 (timm ByobNet `resnet50_clip.openai`): stem.conv{1,2,3}.{conv,bn}, stages.{s}.{b}.*, head.*
+def _cna(cin, cout, k, stride=1):
+    t = ParamTree()
+    t.conv, t.bn = _conv(cin, cout, k, stride), nn.BatchNorm2d(cout)
+    return t
+
+
+def clip_resnet50_tree() -> nn.Module:
+    root = ParamTree()
+    stem = ParamTree()
+    stem.conv1, stem.conv2, stem.conv3 = _cna(3, 32, 3, 2), _cna(32, 32, 3), _cna(32, 64, 3)
+    stem.pool = nn.AvgPool2d(2)
+    root.stem = stem
+    stages, cin = [], 64
+    for si, (planes, blocks, _) in enumerate(RESNET50_STAGES):
+        blks = []
+        for b in range(blocks):
+            blk = ParamTree()
+            stride = 2 if (b == 0 and si > 0) else 1
+            if b == 0:
+                sc = ParamTree()
+                sc.pool = nn.AvgPool2d(stride) if stride > 1 else nn.Identity()
+                sc.conv = _cna(cin, planes * 4, 1)
+                blk.shortcut = sc
+            blk.conv1_1x1 = _cna(cin, planes, 1)
+            blk.conv2_kxk = _cna(planes, planes, 3)
+            blk.conv2_kxk.aa = nn.AvgPool2d(stride) if stride > 1 else nn.Identity()
+            blk.conv3_1x1 = _cna(planes, planes * 4, 1)
+            blk.act = nn.ReLU()
+            blks.append(blk)
+            cin = planes * 4
+        stages.append(_seq(blks))
+    root.stages = _seq(stages)
+    head = ParamTree()  # attention pool: dead for the score, kept for state_dict parity
+    head.pos_embed = nn.Parameter(torch.randn(50, 2048) / 2048 ** 0.5)
+    head.q, head.k, head.v, head.proj = nn.Linear(2048, 2048), nn.Linear(2048, 2048), nn.Linear(2048, 2048), nn.Linear(2048, 1024)
+    root.head = head
+    root.pretrained_cfg = {"input_size": (3, 224, 224), "interpolation": "bicubic", "crop_pct": 1.0,
+                           "mean": (0.48145466, 0.4578275, 0.40821073), "std": (0.26862954, 0.26130258, 0.27577711)}
+    return root
+
+
+TREES = {"resnet50": resnet50_tree, "resnet50_clip.openai": clip_resnet50_tree}
+
+
+def trunk_family(clip_name: str) -> str:
+    base = clip_name.split(".")[0]
+    if base == "resnet50":
+        return "resnet50"
+    if base == "resnet50_clip":
+        return "resnet50_clip.openai"
+    raise ValueError(f"trunk {clip_name!r} is not supported by the B200 scorer (resnet50, resnet50_clip.openai)")
+
+
+def create_trunk(clip_name: str, seed: int = 0) -> nn.Module:
+    """timm.create_model(clip_name, pretrained=True) when a real timm is installed, else a seeded random tree."""
+    family = trunk_family(clip_name)
+    try:
+        import timm  # noqa: PLC0415
+
+        if getattr(timm, "__version__", None):  # a real install, not a test shim
+            return timm.create_model(clip_name, pretrained=True)
+    except ImportError:
+        pass
+    with torch.random.fork_rng():
+        torch.manual_seed(seed)
+        tree = TREES[family]()
+        for m in tree.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+    return tree
+
+
+# ---------------------------------------------------------------------------------------------
+# lowering: module tree -> op list with folded weights
+# ---------------------------------------------------------------------------------------------
+
+def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d, cin_pad: int | None = None):
+    """conv (no bias) followed by eval-mode BatchNorm -> (weight [Cout,KH,KW,Cin_pad] fp64, bias [Cout] fp64)."""
+    w = conv.weight.detach().double().cpu()
+    gamma, beta = bn.weight.detach().double().cpu(), bn.bias.detach().double().cpu()
+    mean, var = bn.running_mean.detach().double().cpu(), bn.running_var.detach().double().cpu()
+    scale = gamma / torch.sqrt(var + bn.eps)
+    w = (w * scale[:, None, None, None]).permute(0, 2, 3, 1).contiguous()
+    if cin_pad is not None and cin_pad > w.shape[-1]:
+        w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
+    return w, beta - mean * scale
+
+
+class Program:
+    """Ops in execution order; `weights` holds (w fp64, b fp64) per conv op index."""
+
+    def __init__(self):
+        self.ops: list[dict] = []
+        self.n_bufs = 0
+        self.flops_per_image_224 = 0
+
+    def conv(self, conv, bn, src, dst, res=-1, relu=True, cin_pad=None):
+        w, b = fold_conv_bn(conv, bn, cin_pad)
+        self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=res, cin=w.shape[3], cout=w.shape[0],
+                             kh=w.shape[1], kw=w.shape[2], stride=conv.stride[0], pad=conv.padding[0],
+                             relu=int(relu), tap=-1, w=w, b=b, true_cin=conv.in_channels))
+
+    def pool(self, kind, src, dst, window):
+        self.ops.append(dict(kind=kind, src=src, dst=dst, res=-1, cin=0, cout=0, kh=window, kw=window, stride=window,
+                             pad=0, relu=0, tap=-1, w=None, b=None))
+
+    def tap(self, src, j):
+        self.ops.append(dict(kind=_lib.OP_TAP, src=src, dst=-1, res=-1, cin=0, cout=0, kh=0, kw=0, stride=0, pad=0,
+                             relu=0, tap=j, w=None, b=None))
+
+
+def lower_resnet50(clip: nn.Module, depth: int) -> Program:
+    """timm resnet50; taps = layer{s}.2.act3 for s in range(4-depth, 5)  (global_eval_models.py:701)."""
+    P = Program()
+    IN, A, B, T1, T2, DS = range(6)
+    P.n_bufs = 6
+    P.conv(clip.conv1, clip.bn1, IN, T1, cin_pad=8)
+    P.pool(_lib.OP_MAXPOOL3S2, T1, A, 3)
+    x = A
+    for li in range(1, 5):
+        layer = getattr(clip, f"layer{li}")
+        for bi, blk in enumerate(layer.children()):
+            y = B if x == A else A
+            P.conv(blk.conv1, blk.bn1, x, T1)
+            P.conv(blk.conv2, blk.bn2, T1, T2)
+            res = x
+            ds = getattr(blk, "downsample", None)
+            if ds is not None:
+                dconv, dbn = list(ds.children())[:2]
+                P.conv(dconv, dbn, x, DS, relu=False)
+                res = DS
+            P.conv(blk.conv3, blk.bn3, T2, y, res=res)
+            x = y
+            if bi == 2 and li >= 4 - depth:
+                P.tap(x, li - (4 - depth))
+    return P
+
+
+def lower_clip_resnet50(clip: nn.Module, depth: int) -> Program:
+    """timm resnet50_clip.openai; taps = stages.{s}.2.act for s in range(3-depth, 4)  (global_eval_models.py:327)."""
+    P = Program()
+    IN, A, B, T1, T2, T3, D0, DS = range(8)
+    P.n_bufs = 8
+    st = clip.stem
+    P.conv(st.conv1.conv, st.conv1.bn, IN, T1, cin_pad=8)
+    P.conv(st.conv2.conv, st.conv2.bn, T1, T2)
+    P.conv(st.conv3.conv, st.conv3.bn, T2, T1)
+    P.pool(_lib.OP_AVGPOOL, T1, A, 2)
+    x = A
+    for si, stage in enumerate(clip.stages.children()):
+        for bi, blk in enumerate(stage.children()):
+            y = B if x == A else A
+            stride = 2 if (bi == 0 and si > 0) else 1
+            P.conv(blk.conv1_1x1.conv, blk.conv1_1x1.bn, x, T1)
+            P.conv(blk.conv2_kxk.conv, blk.conv2_kxk.bn, T1, T2)
+            mid = T2
+            if stride > 1:
+                P.pool(_lib.OP_AVGPOOL, T2, T3, stride)
+                mid = T3
+            res = x
+            sc = getattr(blk, "shortcut", None)
+            if sc is not None:
+                sx = x
+                if stride > 1:
+                    P.pool(_lib.OP_AVGPOOL, x, D0, stride)
+                    sx = D0
+                P.conv(sc.conv.conv, sc.conv.bn, sx, DS, relu=False)
+                res = DS
+            P.conv(blk.conv3_1x1.conv, blk.conv3_1x1.bn, mid, y, res=res)
+            x = y
+            if bi == 2 and si >= 3 - depth:
+                P.tap(x, si - (3 - depth))
+    return P
+
+
+LOWER = {"resnet50": lower_resnet50, "resnet50_clip.openai": lower_clip_resnet50}
+
+
+def conv_flops(program: Program, H: int, W: int) -> int:
+    """Algorithmic FLOPs (2*MAC, unpadded Cin) of the conv ops for ONE HxW image."""
+    shapes = {0: (H, W)}
+    total = 0
+    for op in program.ops:
+        h, w = shapes[op["src"]]
+        if op["kind"] == _lib.OP_CONV:
+            oh = (h + 2 * op["pad"] - op["kh"]) // op["stride"] + 1
+            ow = (w + 2 * op["pad"] - op["kw"]) // op["stride"] + 1
+            total += 2 * oh * ow * op["cout"] * op["kh"] * op["kw"] * op["true_cin"]
+            shapes[op["dst"]] = (oh, ow)
+        elif op["kind"] == _lib.OP_MAXPOOL3S2:
+            shapes[op["dst"]] = ((h - 1) // 2 + 1, (w - 1) // 2 + 1)
+        elif op["kind"] == _lib.OP_AVGPOOL:
+            shapes[op["dst"]] = (h // op["stride"], w // op["stride"])
+    return total

@@ -1,0 +1,52 @@
+"""Test helpers: call the C-ABI (include/semdiff_b200.h) on torch tensors."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from semdiff_b200 import _lib
+
+DT = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}
+
+
+def lib():
+    return _lib.load()
+
+
+def sp():
+    return _lib.stream_ptr()
+
+
+def nhwc(x: torch.Tensor, dtype) -> torch.Tensor:
+    """NCHW fp32 -> contiguous NHWC in `dtype`."""
+    return x.permute(0, 2, 3, 1).contiguous().to(dtype)
+
+
+def nchw(x: torch.Tensor) -> torch.Tensor:
+    return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+def conv2d(x_nhwc, w_ohwi, bias, residual, stride, pad, relu, precision: str, impl: int):
+    n, H, W, cin = x_nhwc.shape
+    cout, kh, kw, _ = w_ohwi.shape
+    oh, ow = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    out = torch.empty(n, oh, ow, cout, dtype=x_nhwc.dtype, device=x_nhwc.device)
+    rc = lib().semdiff_conv2d(x_nhwc.data_ptr(), w_ohwi.data_ptr(), bias.data_ptr(),
+                              residual.data_ptr() if residual is not None else None, out.data_ptr(), n, H, W, cin, cout,
+                              kh, kw, stride, pad, int(relu), _lib.PRECISIONS[precision], impl, sp())
+    _lib.check(rc, "semdiff_conv2d")
+    return out
+
+
+def conv_reference(x_nhwc, w_ohwi, bias, residual, stride, pad, relu):
+    """fp32 torch reference on the SAME (already rounded) operands."""
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    y = torch.nn.functional.conv2d(nchw(x_nhwc).double(), w_ohwi.double().permute(0, 3, 1, 2), bias.double(),
+                                   stride=stride, padding=pad)
+    if residual is not None:
+        y = y + nchw(residual).double()
+    if relu:
+        y = torch.relu(y)
+    return y.permute(0, 2, 3, 1).contiguous()

@@ -1,0 +1,41 @@
+"""GPU parity of the tcgen05/TMEM/TMA implicit-GEMM conv (csrc/conv_tc.cu) against an fp64 torch conv on the
+same 16-bit operands.  Tolerance: fp32 accumulation of <= 4608 products of O(1) terms, then ONE rounding to the
+16-bit output type: |err| <= 2^-8 * |ref| + 2e-3 for bf16 (2^-11 for fp16)."""
+import pytest
+import torch
+
+from semdiff_b200 import _lib
+from test_kernels_gpu import CONV_CASES, _conv_case
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(out, ref, precision):
+    rel = 2.0 ** -8 if precision == "bf16" else 2.0 ** -11
+    bad = (out - ref).abs() > rel * ref.abs() + 2e-3
+    assert not bad.any(), f"{int(bad.sum())} / {bad.numel()} mismatches, max abs err {(out - ref).abs().max().item():.4g}"
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_tc_gather(case, precision):
+    out, ref = _conv_case(case, precision, _lib.CONV_TC_GATHER)
+    _check(out, ref, precision)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[5] == 1 and c[6] == 1 and c[3] % 64 == 0])
+def test_conv_tc_tma(case, precision):
+    out, ref = _conv_case(case, precision, _lib.CONV_TC_TMA)
+    _check(out, ref, precision)
+
+
+def test_conv_tc_many_tiles_persistent():
+    """More tiles than SMs: exercises the persistent loop, both TMEM accumulator stages and smem ring wrap."""
+    case = (8, 56, 56, 64, 256, 1, 1, 0, True)     # M = 25088 -> 196 m-tiles x 1 n-tile
+    for impl in (_lib.CONV_TC_TMA, _lib.CONV_TC_GATHER):
+        out, ref = _conv_case(case, "bf16", impl, seed=3)
+        _check(out, ref, "bf16")
+    case = (4, 28, 28, 128, 128, 3, 1, 1, False)   # K = 1152 -> 18 k-blocks per tile
+    out, ref = _conv_case(case, "bf16", _lib.CONV_TC_GATHER, seed=4)
+    _check(out, ref, "bf16")
