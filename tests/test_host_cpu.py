@@ -1,0 +1,91 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every declared symbol, the parameter trees keep
+the reference's state_dict layout, BatchNorm folding and lowering are correct, and the product refuses to run
+without a GPU (no fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+import semdiff_b200
+from oracle.trunks import build_trunk
+from semdiff_b200 import _lib, trunks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    with open(os.path.join(ROOT, "include", "semdiff_b200.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(semdiff_[a-z0-9_]+)\s*\(", header))
+    declared -= {"semdiff_stream_t"}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.semdiff_version()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "measuring-semantic-differences-in-the-super-resolution-domain_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+@pytest.mark.parametrize("name", ["resnet50", "resnet50_clip.openai"])
+def test_state_dict_layout_matches_oracle_trunk(name):
+    mine, ref = trunks.create_trunk(name), build_trunk(name, calibrate_bn=False)
+    assert list(mine.state_dict().keys()) == list(ref.state_dict().keys())
+    for k, v in ref.state_dict().items():
+        assert mine.state_dict()[k].shape == v.shape, k
+    with pytest.raises(RuntimeError):
+        mine(torch.zeros(1, 3, 224, 224))   # parameter container only: no PyTorch fallback
+
+
+def test_fold_conv_bn_matches_torch():
+    torch.manual_seed(0)
+    conv = torch.nn.Conv2d(3, 16, 7, 2, 3, bias=False).double()
+    bn = torch.nn.BatchNorm2d(16).double()
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    bn.eval()
+    x = torch.randn(2, 3, 20, 20, dtype=torch.double)
+    w, b = trunks.fold_conv_bn(conv, bn, cin_pad=8)
+    assert w.shape == (16, 7, 7, 8) and torch.count_nonzero(w[..., 3:]) == 0
+    y = torch.nn.functional.conv2d(x, w[..., :3].permute(0, 3, 1, 2), b, stride=2, padding=3)
+    assert torch.allclose(y, bn(conv(x)), rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("name,convs,gflop", [("resnet50", 53, 8.174272512), ("resnet50_clip.openai", 55, 10.734452736)])
+def test_lowering(name, convs, gflop):
+    tree = trunks.create_trunk(name)
+    for depth in range(4):
+        prog = trunks.LOWER[name](tree, depth)
+        assert sum(op["kind"] == _lib.OP_CONV for op in prog.ops) == convs
+        taps = [op["tap"] for op in prog.ops if op["kind"] == _lib.OP_TAP]
+        assert taps == list(range(depth + 1))
+        for op in prog.ops:   # a conv never reads or adds the buffer it writes
+            if op["kind"] != _lib.OP_TAP:
+                assert op["dst"] not in (op["src"], op["res"]) and 0 < op["dst"] < prog.n_bufs
+    assert abs(trunks.conv_flops(prog, 224, 224) / 1e9 - gflop) < 1e-9   # SURVEY.md 8d algorithmic FLOPs
+
+
+def test_no_cpu_fallback_and_argument_checks():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        semdiff_b200.CLIP_lpips_stages_cnn_clsbckb(clip_name="resnet50", depth=3, device="cpu")
+    with pytest.raises(ValueError):
+        trunks.trunk_family("vit_base_patch16_clip_224.openai")
+
+
+def test_plan_api_rejects_bad_arguments_without_gpu():
+    lib = _lib.load()
+    import ctypes as C
+    handle = C.c_void_p()
+    assert lib.semdiff_plan_create(None, 0, 0, 0, C.byref(handle)) == -1
+    assert b"bad arguments" in lib.semdiff_last_error()
+    assert lib.semdiff_distance_parts(56 * 56, 256) == 25 and lib.semdiff_distance_parts(49, 2048) == 4
+    assert lib.semdiff_distance_parts(1, 8) == 1 and lib.semdiff_distance_parts(1024 * 1024, 256) == 64
