@@ -224,6 +224,51 @@ class _B200Scorer(nn.Module):
         return out, pre, chan
 
 
+    @torch.no_grad()
+    def score_host(self, gt_host: torch.Tensor, sr_host: torch.Tensor, out_host: torch.Tensor | None = None,
+                   chunk_pairs: int = 64) -> torch.Tensor:
+        """End-to-end scoring of HOST tensors (pinned fp32 [N,3,H,W]) -> host scores [N].
+
+        The images cross PCIe in chunks on a copy stream into two staging buffers while the previous chunk is
+        scored on the current stream, so the transfer overlaps the kernels; the call returns once the scores are
+        on the host.  Chunking does not change any pair's arithmetic."""
+        n, _, H, W = gt_host.shape
+        dev = self._device
+        if out_host is None:
+            out_host = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        if n == 0:
+            return out_host
+        head_w = torch.cat([m.weight.reshape(-1) for m in self.w_layers]).float()
+        head_b = torch.cat([m.bias.reshape(-1) for m in self.w_layers]).float()
+        chunk = min(chunk_pairs, n)
+        if getattr(self, "_stage_shape", None) != (chunk, H, W):
+            self._stage = [(torch.empty(chunk, 3, H, W, device=dev), torch.empty(chunk, 3, H, W, device=dev)) for _ in range(2)]
+            self._stage_shape = (chunk, H, W)
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        out_dev = torch.empty(n, dtype=torch.float32, device=dev)
+        main = torch.cuda.current_stream(dev)
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        n_chunks = (n + chunk - 1) // chunk
+        for i in range(n_chunks):
+            lo, hi = i * chunk, min(n, (i + 1) * chunk)
+            g_buf, s_buf = self._stage[i % 2]
+            with torch.cuda.stream(self._copy_stream):
+                if i >= 2:
+                    self._copy_stream.wait_event(consumed[i % 2])
+                else:
+                    self._copy_stream.wait_stream(main)
+                g_buf[: hi - lo].copy_(gt_host[lo:hi], non_blocking=True)
+                s_buf[: hi - lo].copy_(sr_host[lo:hi], non_blocking=True)
+                copied[i % 2].record(self._copy_stream)
+            main.wait_event(copied[i % 2])
+            out_dev[lo:hi] = self._run(g_buf[: hi - lo], s_buf[: hi - lo], head_w, head_b)[0]
+            consumed[i % 2].record(main)
+        out_host.copy_(out_dev, non_blocking=True)
+        main.synchronize()
+        return out_host
+
+
 class CLIP_lpips_stages_cnn(_B200Scorer):
     """timm ByobNet `resnet50_clip.openai` trunk; taps stages.{s}.2.act (reference :308-429)."""
 
