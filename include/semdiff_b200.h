@@ -37,7 +37,7 @@ enum {
   SEMDIFF_CONV_AUTO = 0,
   SEMDIFF_CONV_SIMT = 1,      /* CUDA-core implicit GEMM, any precision (the only fp32 path) */
   SEMDIFF_CONV_TC_GATHER = 2, /* tcgen05 + cp.async software im2col (any k/stride/pad, Cin % 8 == 0) */
-  SEMDIFF_CONV_TC_TMA = 3     /* tcgen05 + TMA tiled loads (1x1 stride 1) */
+  SEMDIFF_CONV_TC_TMA = 3     /* tcgen05 + TMA activations: tiled loads for 1x1 stride 1, im2col mode otherwise (Cin % 64 == 0) */
 };
 
 /* One step of the trunk program.  Buffers are logical ids in [0, n_bufs); buffer 0 is the packed

@@ -8,12 +8,17 @@
 // into Wt / bias on the host, GT and SR images share one launch.
 //
 // CTA = one 128 x BLOCK_N output tile at a time, persistent over tiles, warp-specialised:
-//   warp 0      TMA producer: weight tile (always) and, for 1x1 stride-1 convs, the activation tile
+//   warp 0      TMA producer: weight tile (always) + activation tile:
+//                 A_TMA     1x1 stride-1 convs: plain 2-D tiled loads of [M, Cin]
+//                 A_IM2COL  kxk / strided convs with Cin % 64 == 0: TMA im2col mode over the NHWC tensor
 //   warp 1      tcgen05.mma issuer (one thread); owns the TMEM allocation (2 accumulator stages)
-//   warps 2-5   epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> 16-bit -> global
-//   warps 6-9   (gather variant) software im2col: cp.async 16 B chunks into the 128B-swizzled A tile,
-//               zero-filling padding / M tail / K tail
-// Pipelines: smem ring full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue).
+//   warps 2-5   epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> 16-bit -> swizzled smem -> TMA store
+//   warp 6      residual loader: TMA-prefetches the residual tile into the smem slot the epilogue will
+//               overwrite in place with the result (ring of slots, freed when the store has read them)
+//   warps 6-9   (A_GATHER only; the residual loader is then warp 10) software im2col for Cin < 64 (stems): cp.async 16 B chunks into the swizzled
+//               A tile, zero-filling padding / M tail / K tail
+// Pipelines: smem ring full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue),
+//            C ring res_full/c_free (residual loader <-> epilogue/TMA store).
 #include <cuda.h>
 
 #include "common.cuh"
@@ -24,55 +29,80 @@ namespace semdiff {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int GATHER_LAG = 2;  // cp.async groups kept in flight per gather thread
+enum { A_TMA = 0, A_GATHER = 1, A_IM2COL = 2 };
 
 template <int BLOCK_N> struct TcCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int STAGES = BLOCK_N >= 128 ? 4 : 6;
+  static constexpr int GATHER_LAG = STAGES - 2;        // cp.async groups in flight per gather thread
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // + slack for 1024 B alignment
+  // epilogue staging: the tile is written out in column groups, each group = BOXES TMA boxes of BOX_COLS columns
+  static constexpr int BOX_COLS = BLOCK_N < 64 ? BLOCK_N : 64;
+  static constexpr int GROUP_COLS = BLOCK_N < 128 ? BLOCK_N : 128;
+  static constexpr int GROUPS = BLOCK_N / GROUP_COLS;
+  static constexpr int BOXES = GROUP_COLS / BOX_COLS;   // per group
+  static constexpr int BOX_BYTES = BLOCK_M * BOX_COLS * 2;
+  static constexpr int GROUP_BYTES = BOXES * BOX_BYTES;
+  static constexpr int RING = BLOCK_N == 256 ? 1 : 3;   // BLOCK_N == 256 never carries a residual
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RING;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING * GROUP_BYTES + NUM_BARS * 8 + 16 + 1024;
 };
 
 struct alignas(64) ConvTcParams {
-  CUtensorMap tmA;  // activations as [M, Cin] (TMA variant only)
+  CUtensorMap tmA;  // activations: [M, Cin] tiled (A_TMA) or NHWC im2col (A_IM2COL)
   CUtensorMap tmB;  // weights as [Cout, K]
+  CUtensorMap tmC;  // output as [M, Cout]
+  CUtensorMap tmR;  // residual as [M, Cout]
   const void* in;
-  const void* res;
-  void* out;
   const float* bias;
-  int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, relu;
+  int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, relu, has_res;
   int M, num_kb, m_tiles, n_tiles, cpt, taps;
 };
+static_assert(sizeof(ConvTcParams) <= 768, "ConvTcLaunch::params too small");
 
-template <typename T, int BLOCK_N, bool kTmaA>
-__global__ void __launch_bounds__(kTmaA ? 192 : 320, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+// 16-byte chunk position inside a swizzled row of ROW_BYTES (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B)
+template <int ROW_BYTES> __device__ __forceinline__ uint32_t swz_chunk(uint32_t chunk, uint32_t row) {
+  if constexpr (ROW_BYTES == 128) return chunk ^ (row & 7);
+  else return chunk ^ ((row >> 1) & 3);
+}
+
+template <typename T, int BLOCK_N, int kAMode>
+__global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_c = smem + STAGES * Cfg::STAGE_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + RING * Cfg::GROUP_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_full_bar = tmem_empty_bar + 2;
+  uint64_t* c_free_bar = res_full_bar + RING;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c_free_bar + RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
-    if (kTmaA) tma_prefetch_desc(&p.tmA);
+    if (kAMode != A_GATHER) tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    tma_prefetch_desc(&p.tmC);
+    if (p.has_res) tma_prefetch_desc(&p.tmR);
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(&full_bar[i], kTmaA ? 1 : 1 + 4);
+      mbar_init(&full_bar[i], kAMode == A_GATHER ? 1 + 4 : 1);
       mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 4);
+    }
+    for (int i = 0; i < RING; ++i) {
+      mbar_init(&res_full_bar[i], 1);
+      mbar_init(&c_free_bar[i], 1);
     }
     mbar_fence_init();
   }
@@ -86,12 +116,30 @@ __global__ void __launch_bounds__(kTmaA ? 192 : 320, 1) conv_tc_kernel(const __g
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0, phase = 0;
+      const int kb_per_tap = p.Cin >> 6;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        int n = 0, h0 = 0, w0 = 0;
+        if (kAMode == A_IM2COL) {
+          const int gm = m_tile * BLOCK_M;
+          n = gm / (p.OH * p.OW);
+          const int r = gm - n * p.OH * p.OW;
+          const int oh = r / p.OW, ow = r - oh * p.OW;
+          h0 = oh * p.stride - p.pad;
+          w0 = ow * p.stride - p.pad;
+        }
+        int tap = 0, cb = 0;  // filter tap and 64-channel block of the current k-block (im2col)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_STAGE_BYTES + (kTmaA ? A_STAGE_BYTES : 0));
-          if (kTmaA) tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_STAGE_BYTES + (kAMode != A_GATHER ? A_STAGE_BYTES : 0));
+          if (kAMode == A_TMA) {
+            tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
+          } else if (kAMode == A_IM2COL) {
+            const int r = tap / p.KW, s = tap - r * p.KW;
+            tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, cb * BLOCK_K, w0, h0, n,
+                               (uint16_t)s, (uint16_t)r);
+            if (++cb == kb_per_tap) { cb = 0; ++tap; }
+          }
           tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -125,37 +173,61 @@ __global__ void __launch_bounds__(kTmaA ? 192 : 320, 1) conv_tc_kernel(const __g
     }
   } else if (warp < 6) {
     // ===================== epilogue =====================
+    constexpr int ROW_BYTES = Cfg::BOX_COLS * 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
-    const T* res = reinterpret_cast<const T*>(p.res);
-    T* out = reinterpret_cast<T*>(p.out);
-    int local = 0;
+    const bool store_thread = (warp == 2 && lane == 0);
+    int local = 0, gc = 0;  // gc: running column-group counter of this CTA (ring position)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tcgen05_fence_after();
-      const int gm = m_tile * BLOCK_M + row;
-      const bool ok = gm < p.M;
+      bool tmem_ready = false;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + c * 32, v);
-        tmem_ld_wait();
-        if (ok) {
-          const int col0 = n_tile * BLOCK_N + c * 32;
-          const int64_t off = (int64_t)gm * p.Cout + col0;
+      for (int g = 0; g < Cfg::GROUPS; ++g, ++gc) {
+        const int slot = gc % RING;
+        uint8_t* cbuf = smem_c + slot * Cfg::GROUP_BYTES;
+        if (p.has_res) {
+          mbar_wait(&res_full_bar[slot], (gc / RING) & 1);  // residual landed (and the slot is ours)
+        } else {
+          if (store_thread) bulk_wait_read<RING - 1>();      // the store that last used this slot has read it
+          named_bar_sync(1, 128);
+        }
+        if (!tmem_ready) {
+          mbar_wait(&tmem_full_bar[acc], acc_phase);
+          tcgen05_fence_after();
+          tmem_ready = true;
+        }
+#pragma unroll 1
+        for (int b = 0; b < Cfg::BOXES; ++b) {
+          const int col_in_tile = g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS;
+          uint32_t v[Cfg::BOX_COLS];
+          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + col_in_tile;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
+          for (int h = 0; h < Cfg::BOX_COLS / 32; ++h)
+            tmem_ld_32x32b_x32(taddr + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
+          tmem_ld_wait();
+          if (g == Cfg::GROUPS - 1 && b == Cfg::BOXES - 1) {
+            // every TMEM read of this accumulator stage has retired: hand it back to the MMA warp early
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          const int col0 = n_tile * BLOCK_N + col_in_tile;
+          const uint32_t row_addr = smem_u32(cbuf + b * Cfg::BOX_BYTES) + row * ROW_BYTES;
+#pragma unroll
+          for (int j = 0; j < Cfg::BOX_COLS / 8; ++j) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
             float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
                           __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
                           __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
                           __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
-            if (res != nullptr) {
+            const uint32_t addr = row_addr + (swz_chunk<ROW_BYTES>(j, row) << 4);
+            if (p.has_res) {
+              uint4 rq;
+              asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rq.x), "=r"(rq.y), "=r"(rq.z), "=r"(rq.w) : "r"(addr));
               float r[8];
-              unpack8<T>(*reinterpret_cast<const uint4*>(res + off + j * 8), r);
+              unpack8<T>(rq, r);
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] += r[e];
             }
@@ -163,16 +235,47 @@ __global__ void __launch_bounds__(kTmaA ? 192 : 320, 1) conv_tc_kernel(const __g
 #pragma unroll
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
             }
-            *reinterpret_cast<uint4*>(out + off + j * 8) = pack8<T>(f);
+            const uint4 o = pack8<T>(f);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store (async proxy)
+        named_bar_sync(1, 128);
+        if (store_thread) {
+#pragma unroll
+          for (int b = 0; b < Cfg::BOXES; ++b)
+            tma_store_2d(&p.tmC, cbuf + b * Cfg::BOX_BYTES, n_tile * BLOCK_N + g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
+                         m_tile * BLOCK_M);
+          bulk_commit();
+          if (p.has_res && RING > 1) {
+            bulk_wait_read<1>();  // every store but the one just issued has read its slot
+            if (gc >= 1) mbar_arrive(&c_free_bar[(gc - 1) % RING]);
           }
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
     }
-  } else if (!kTmaA) {
+    if (store_thread) bulk_wait<0>();  // smem must stay valid until the last store has completed
+  } else if (warp == (kAMode == A_GATHER ? 10 : 6)) {
+    // ===================== residual loader =====================
+    if (lane == 0 && p.has_res) {
+      int gc = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        for (int g = 0; g < Cfg::GROUPS; ++g, ++gc) {
+          const int slot = gc % RING;
+          mbar_wait(&c_free_bar[slot], ((gc / RING) & 1) ^ 1);
+          mbar_arrive_expect_tx(&res_full_bar[slot], Cfg::GROUP_BYTES);
+          uint8_t* cbuf = smem_c + slot * Cfg::GROUP_BYTES;
+#pragma unroll
+          for (int b = 0; b < Cfg::BOXES; ++b)
+            tma_load_2d(&p.tmR, &res_full_bar[slot], cbuf + b * Cfg::BOX_BYTES,
+                        n_tile * BLOCK_N + g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS, m_tile * BLOCK_M);
+        }
+      }
+    }
+  } else {
     // ===================== software im2col gather (128 threads, one A row each) =====================
+    constexpr int LAG = Cfg::GATHER_LAG;
     const int row = (warp - 6) * 32 + lane;
     const T* in = reinterpret_cast<const T*>(p.in);
     const uint32_t row_off = row * 128, sw = row & 7;
@@ -200,7 +303,7 @@ __global__ void __launch_bounds__(kTmaA ? 192 : 320, 1) conv_tc_kernel(const __g
 #pragma unroll
           for (int j = 0; j < 8; ++j) cp_async_16(dst + ((j ^ sw) << 4), src + (ok ? j * 8 : 0), ok ? 16u : 0u);
         } else {
-          // several taps per k-block (Cin = 8 .. 56): each 16 B chunk is its own (tap, channel group)
+          // several taps per k-block (Cin = 8 .. 32): each 16 B chunk is its own (tap, channel group)
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const int g = kb * 8 + j;
@@ -214,8 +317,8 @@ __global__ void __launch_bounds__(kTmaA ? 192 : 320, 1) conv_tc_kernel(const __g
         }
         cp_async_commit();
         ++issued;
-        if (issued > GATHER_LAG) {
-          cp_async_wait<GATHER_LAG>();
+        if (issued > LAG) {
+          cp_async_wait<LAG>();
           fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
           __syncwarp();
           if (lane == 0) mbar_arrive(&full_bar[arr_stage]);
@@ -227,7 +330,7 @@ __global__ void __launch_bounds__(kTmaA ? 192 : 320, 1) conv_tc_kernel(const __g
     cp_async_wait<0>();
     fence_proxy_async_smem();
     __syncwarp();
-    const int pending = issued < GATHER_LAG ? issued : GATHER_LAG;
+    const int pending = issued < LAG ? issued : LAG;
     for (int i = 0; i < pending; ++i) {
       if (lane == 0) mbar_arrive(&full_bar[arr_stage]);
       if (++arr_stage == STAGES) arr_stage = 0;
@@ -248,51 +351,89 @@ __global__ void __launch_bounds__(kTmaA ? 192 : 320, 1) conv_tc_kernel(const __g
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode_tiled() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(ptr);
-  }
-  return fn;
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                   CUtensorMapFloatOOBfill);
+static void* driver_entry(const char* name) {
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint(name, &ptr, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  return ptr;
+}
+static CUtensorMapDataType tmap_dtype(int precision) {
+  return precision == SEMDIFF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 }
 
-// 2-D K-major 16-bit tensor [rows, cols] (cols contiguous), box = 64 cols x box_rows, 128B swizzle, OOB -> 0
-static int make_tmap_2d(CUtensorMap* m, const void* base, int precision, uint64_t rows, uint64_t cols, uint32_t box_rows) {
-  EncodeTiledFn enc = get_encode_tiled();
+// 2-D 16-bit tensor [rows, cols] (cols contiguous), box = box_cols x box_rows; swizzle span = box_cols * 2 bytes; OOB -> 0
+static int make_tmap_2d(CUtensorMap* m, const void* base, int precision, uint64_t rows, uint64_t cols, uint32_t box_cols,
+                        uint32_t box_rows) {
+  static EncodeTiledFn enc = reinterpret_cast<EncodeTiledFn>(driver_entry("cuTensorMapEncodeTiled"));
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return SEMDIFF_ERR_CUDA; }
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
-  const cuuint32_t box[2] = {BLOCK_K, box_rows};
+  const cuuint32_t box[2] = {box_cols, box_rows};
   const cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapDataType dt = precision == SEMDIFF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-  CUresult r = enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const CUtensorMapSwizzle sw = box_cols * 2 == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  CUresult r = enc(m, tmap_dtype(precision), 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box_rows=%u base=%p", (int)r,
-              (unsigned long long)rows, (unsigned long long)cols, box_rows, base);
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu box=%ux%u base=%p", (int)r,
+              (unsigned long long)rows, (unsigned long long)cols, box_cols, box_rows, base);
     return SEMDIFF_ERR_CUDA;
   }
   return 0;
 }
 
-static int pick_block_n(int cout) {
-  if (cout % 256 == 0) return 256;
-  if (cout % 128 == 0) return 128;
-  if (cout % 64 == 0) return 64;
-  if (cout % 32 == 0) return 32;
+// NHWC activation as (C, W, H, N) in TMA im2col mode: one load = 128 consecutive output pixels x 64 channels of one
+// filter tap.  Corner arithmetic as in CUTLASS's fprop (conv/collective/detail.hpp compute_{lower,upper}_corner_whd):
+// lower = -pad, upper = pad - (k - 1); traversal stride = conv stride.
+static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, const ConvShape& s) {
+  static EncodeIm2colFn enc = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));
+  if (enc == nullptr) { set_error("cuTensorMapEncodeIm2col entry point not found"); return SEMDIFF_ERR_CUDA; }
+  const cuuint64_t dims[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.n_img};
+  const cuuint64_t strides[3] = {(cuuint64_t)s.cin * 2, (cuuint64_t)s.W * s.cin * 2, (cuuint64_t)s.H * s.W * s.cin * 2};
+  const int lower[2] = {-s.pad, -s.pad};
+  const int upper[2] = {s.pad - (s.kw - 1), s.pad - (s.kh - 1)};
+  const cuuint32_t estr[4] = {1, (cuuint32_t)s.stride, (cuuint32_t)s.stride, 1};
+  CUresult r = enc(m, tmap_dtype(precision), 4, const_cast<void*>(base), dims, strides, lower, upper, BLOCK_K, BLOCK_M,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeIm2col failed (%d) n=%d H=%d W=%d C=%d k=%d stride=%d pad=%d", (int)r, s.n_img, s.H, s.W,
+              s.cin, s.kh, s.stride, s.pad);
+    return SEMDIFF_ERR_CUDA;
+  }
+  // Same workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp) for drivers <= 13.1: small tensors
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (uint64_t)s.n_img * s.H * s.W * s.cin * 2 < 131072)
+    reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
   return 0;
+}
+
+static int pick_block_n(int cout, bool has_res, int m_tiles, int sms) {
+  if (cout % 128 != 0) return cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0);
+  if (has_res || cout % 256 != 0) return 128;
+  // 256-wide tiles halve the A re-reads and relieve shared-memory bandwidth, but need enough tiles to fill the SMs
+  return (int64_t)m_tiles * (cout / 256) >= sms ? 256 : 128;
+}
+
+static int a_mode_for(const ConvShape& s, int requested) {
+  const bool pointwise = s.kh == 1 && s.kw == 1 && s.stride == 1 && s.pad == 0 && s.cin % 64 == 0;
+  if (requested == SEMDIFF_CONV_TC_GATHER) return A_GATHER;
+  if (pointwise) return A_TMA;
+  if (s.cin % 64 == 0 && s.pad <= 8 && s.kh <= 9 && s.kw <= 9) return A_IM2COL;
+  return A_GATHER;
 }
 
 bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma) {
   if (precision != SEMDIFF_BF16 && precision != SEMDIFF_FP16) return false;
-  if (s.cin % 8 != 0 || pick_block_n(s.cout) == 0) return false;
+  if (s.cin % 8 != 0 || s.cout % 32 != 0) return false;
   if (s.cin > 64 && s.cin % 64 != 0) return false;
   if (s.cin < 64 && 64 % s.cin != 0) return false;
-  if (use_tma && !(s.kh == 1 && s.kw == 1 && s.stride == 1 && s.pad == 0 && s.cin % 64 == 0)) return false;
+  if (use_tma && s.cin % 64 != 0) return false;
   return s.M() > 0 && s.M() < (int64_t)1 << 31;
 }
 
@@ -307,31 +448,41 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <typename T, int BLOCK_N, bool kTmaA>
+template <typename T, int BLOCK_N, int kAMode>
 static int launch_t(const ConvTcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N>;
   static bool configured = false;
-  auto kern = conv_tc_kernel<T, BLOCK_N, kTmaA>;
+  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode>;
   if (!configured) {
     SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kTmaA ? 192 : 320, Cfg::SMEM_BYTES, st>>>(p);
+  kern<<<grid, kAMode == A_GATHER ? 352 : 224, Cfg::SMEM_BYTES, st>>>(p);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-template <typename T, bool kTmaA>
+template <typename T, int kAMode>
 static int launch_n(const ConvTcParams& p, int block_n, cudaStream_t st) {
   switch (block_n) {
-    case 256: return launch_t<T, 256, kTmaA>(p, st);
-    case 128: return launch_t<T, 128, kTmaA>(p, st);
-    case 64: return launch_t<T, 64, kTmaA>(p, st);
-    case 32: return launch_t<T, 32, kTmaA>(p, st);
+    case 256: return launch_t<T, 256, kAMode>(p, st);
+    case 128: return launch_t<T, 128, kAMode>(p, st);
+    case 64: return launch_t<T, 64, kAMode>(p, st);
+    case 32: return launch_t<T, 32, kAMode>(p, st);
   }
   set_error("conv_tc: unsupported BLOCK_N %d", block_n);
+  return SEMDIFF_ERR_UNSUPPORTED;
+}
+
+template <typename T>
+static int launch_mode(const ConvTcParams& p, int block_n, int a_mode, cudaStream_t st) {
+  switch (a_mode) {
+    case A_TMA: return launch_n<T, A_TMA>(p, block_n, st);
+    case A_GATHER: return launch_n<T, A_GATHER>(p, block_n, st);
+    case A_IM2COL: return launch_n<T, A_IM2COL>(p, block_n, st);
+  }
   return SEMDIFF_ERR_UNSUPPORTED;
 }
 
@@ -345,33 +496,35 @@ int conv_tc_prepare(ConvTcLaunch* L, const void* in, const void* w, const float*
   static_assert(sizeof(ConvTcParams) <= sizeof(L->params), "ConvTcLaunch::params too small");
   ConvTcParams& p = *reinterpret_cast<ConvTcParams*>(L->params);
   memset(&p, 0, sizeof(p));
-  const int block_n = pick_block_n(s.cout);
-  p.in = in; p.res = res; p.out = out; p.bias = bias;
+  const int a_mode = a_mode_for(s, use_tma ? SEMDIFF_CONV_TC_TMA : SEMDIFF_CONV_TC_GATHER);
+  p.M = (int)s.M();
+  p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int block_n = pick_block_n(s.cout, res != nullptr, p.m_tiles, num_sms());
+  if (block_n == 0) { set_error("conv_tc: cout %d not a multiple of 32", s.cout); return SEMDIFF_ERR_UNSUPPORTED; }
+  p.in = in; p.bias = bias; p.has_res = res != nullptr;
   p.H = s.H; p.W = s.W; p.Cin = s.cin; p.OH = s.OH(); p.OW = s.OW(); p.Cout = s.cout;
   p.KH = s.kh; p.KW = s.kw; p.stride = s.stride; p.pad = s.pad; p.relu = s.relu;
-  p.M = (int)s.M();
   p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K;
-  p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.n_tiles = s.cout / block_n;
   p.cpt = s.cin / 8;
   p.taps = s.kh * s.kw;
-  int rc = make_tmap_2d(&p.tmB, w, precision, (uint64_t)s.cout, (uint64_t)s.K(), (uint32_t)block_n);
+  const uint32_t box_cols = block_n < 64 ? block_n : 64;
+  int rc = make_tmap_2d(&p.tmB, w, precision, (uint64_t)s.cout, (uint64_t)s.K(), BLOCK_K, (uint32_t)block_n);
+  if (rc == 0 && a_mode == A_TMA) rc = make_tmap_2d(&p.tmA, in, precision, (uint64_t)p.M, (uint64_t)s.cin, BLOCK_K, BLOCK_M);
+  if (rc == 0 && a_mode == A_IM2COL) rc = make_tmap_im2col(&p.tmA, in, precision, s);
+  if (rc == 0) rc = make_tmap_2d(&p.tmC, out, precision, (uint64_t)p.M, (uint64_t)s.cout, box_cols, BLOCK_M);
+  if (rc == 0 && res != nullptr) rc = make_tmap_2d(&p.tmR, res, precision, (uint64_t)p.M, (uint64_t)s.cout, box_cols, BLOCK_M);
   if (rc != 0) return rc;
-  if (use_tma) {
-    rc = make_tmap_2d(&p.tmA, in, precision, (uint64_t)p.M, (uint64_t)s.cin, BLOCK_M);
-    if (rc != 0) return rc;
-  }
   L->block_n = block_n;
-  L->use_tma = use_tma ? 1 : 0;
+  L->a_mode = a_mode;
   L->precision = precision;
   return 0;
 }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t st) {
   const ConvTcParams& p = *reinterpret_cast<const ConvTcParams*>(L->params);
-  if (L->precision == SEMDIFF_BF16)
-    return L->use_tma ? launch_n<__nv_bfloat16, true>(p, L->block_n, st) : launch_n<__nv_bfloat16, false>(p, L->block_n, st);
-  return L->use_tma ? launch_n<__half, true>(p, L->block_n, st) : launch_n<__half, false>(p, L->block_n, st);
+  if (L->precision == SEMDIFF_BF16) return launch_mode<__nv_bfloat16>(p, L->block_n, L->a_mode, st);
+  return launch_mode<__half>(p, L->block_n, L->a_mode, st);
 }
 
 int launch_conv_tc(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,

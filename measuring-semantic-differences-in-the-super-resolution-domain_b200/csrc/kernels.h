@@ -25,14 +25,15 @@ int launch_avgpool(const void* in, void* out, int n_img, int H, int W, int c, in
                    cudaStream_t stream);
 int launch_conv_simt(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
                      int precision, cudaStream_t stream);
-// tcgen05 path; use_tma selects the TMA-tiled A producer (1x1 stride 1 only) over the cp.async gather
+// tcgen05 path; use_tma lets the activation tile come through TMA (tiled for 1x1 stride 1, im2col mode otherwise);
+// false forces the cp.async software-im2col gather
 int launch_conv_tc(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
                    int precision, bool use_tma, cudaStream_t stream);
 bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma);
 // prepared launch (TMA descriptors encoded once, reused while pointers and shapes stay the same)
 struct alignas(64) ConvTcLaunch {
-  unsigned char params[512];
-  int block_n, use_tma, precision;
+  unsigned char params[768];
+  int block_n, a_mode, precision;
 };
 int conv_tc_prepare(ConvTcLaunch* L, const void* in, const void* w, const float* bias, const void* res, void* out,
                     const ConvShape& s, int precision, bool use_tma);

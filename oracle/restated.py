@@ -26,6 +26,7 @@ class RestatedScorer(nn.Module):
         super().__init__()
         self.clip = build_trunk(trunk, seed=seed, calibrate_bn=calibrate_bn)
         self.depth = depth
+        self.trunk_name = trunk
         self.wanted_layers = tap_names(trunk, depth)
         torch.manual_seed(seed + 1000)  # same stream as reference_loader.build_reference_scorer
         self.w_layers = nn.ModuleList(

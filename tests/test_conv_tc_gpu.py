@@ -23,8 +23,19 @@ def test_conv_tc_gather(case, precision):
     _check(out, ref, precision)
 
 
+IM2COL_CASES = [
+    # n, H, W, cin, cout, k, stride, pad, residual  (TMA im2col mode: anything but 1x1 stride 1, Cin % 64 == 0)
+    (2, 56, 56, 64, 64, 3, 1, 1, False),      # tiles span image rows and image boundaries
+    (3, 56, 40, 128, 128, 3, 2, 1, False),    # H != W, stride 2
+    (5, 7, 7, 512, 512, 3, 1, 1, False),      # M = 245: tile crosses several images, ragged tail
+    (2, 14, 14, 1024, 2048, 1, 2, 0, False),  # strided 1x1
+    (1, 9, 9, 64, 64, 3, 1, 1, False),        # tensor < 128 KiB (descriptor workaround path)
+    (2, 15, 15, 64, 128, 3, 2, 1, False),     # odd size, stride 2
+]
+
+
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
-@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[5] == 1 and c[6] == 1 and c[3] % 64 == 0])
+@pytest.mark.parametrize("case", [c for c in CONV_CASES if c[3] % 64 == 0] + IM2COL_CASES)
 def test_conv_tc_tma(case, precision):
     out, ref = _conv_case(case, precision, _lib.CONV_TC_TMA)
     _check(out, ref, precision)

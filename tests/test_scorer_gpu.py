@@ -51,8 +51,9 @@ def test_fp32_mode_matches_oracle(trunk):
 def torch_16bit_error(oracle, gt, sr, ref, dtype):
     """The same oracle module run by PyTorch/cuDNN itself in `dtype` (channels_last) on this GPU: the yardstick for
     what 16-bit storage costs on these weights."""
-    import copy
-    m = copy.deepcopy(oracle).cuda().to(dtype).to(memory_format=torch.channels_last)
+    m = RestatedScorer(oracle.trunk_name, oracle.depth, seed=0)   # fresh module: forward hooks do not deep-copy
+    m.load_state_dict(oracle.state_dict())
+    m = m.cuda().to(dtype).to(memory_format=torch.channels_last)
     with torch.no_grad():
         got = m(gt.cuda().to(dtype).contiguous(memory_format=torch.channels_last),
                 sr.cuda().to(dtype).contiguous(memory_format=torch.channels_last)).float().cpu()
