@@ -40,6 +40,12 @@ enum {
   SEMDIFF_CONV_TC_TMA = 3     /* tcgen05 + TMA activations: tiled loads for 1x1 stride 1, im2col mode otherwise (Cin % 64 == 0) */
 };
 
+/* layout of buffer 0 (what the pack kernel makes of the fp32 NCHW images) */
+enum {
+  SEMDIFF_INPUT_NHWC8 = 0,    /* [2n, H, W, 8], channels 3..7 zero */
+  SEMDIFF_INPUT_S2D_ROW4 = 1  /* [2n, H/2+3, W/2, 64]: 2x2 space-to-depth row windows for 7x7/2 stems (elementwise.cu) */
+};
+
 /* One step of the trunk program.  Buffers are logical ids in [0, n_bufs); buffer 0 is the packed
  * input image batch.  The program is what /root/reference/models/global_eval_models.py:364,371
  * (self.clip(a), self.clip(b)) executes inside timm, with BatchNorm folded. */
@@ -65,7 +71,7 @@ typedef struct semdiff_plan semdiff_plan;
 
 /* Build an execution plan for a trunk program.  Copies the op list (not the weights). */
 int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision,
-                        semdiff_plan** out_plan);
+                        int32_t input_layout, semdiff_plan** out_plan);
 int semdiff_plan_destroy(semdiff_plan* plan);
 /* Force the conv implementation of every conv op (SEMDIFF_CONV_*; AUTO = best supported). Testing aid. */
 int semdiff_plan_set_conv_impl(semdiff_plan* plan, int32_t impl);
@@ -97,9 +103,9 @@ int64_t semdiff_plan_last_launches(const semdiff_plan* plan);
 
 /* ---- single kernels (unit tests call these; the plan calls the same launchers) ------------- */
 
-/* fp32 NCHW [n,3,H,W] x2 -> NHWC [2n,H,W,8] (channels 3..7 zero), GT images first */
-int semdiff_pack_nhwc(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
-                      int32_t precision, semdiff_stream_t stream);
+/* fp32 NCHW [n,3,H,W] x2 -> buffer 0 in `layout` (SEMDIFF_INPUT_*), GT images first */
+int semdiff_pack_input(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
+                       int32_t precision, int32_t layout, semdiff_stream_t stream);
 
 /* out = act(conv(in, weight) + bias (+ residual)); NHWC; impl = SEMDIFF_CONV_* */
 int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out,

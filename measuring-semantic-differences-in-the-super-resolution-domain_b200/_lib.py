@@ -14,6 +14,7 @@ PRECISIONS = {"bf16": BF16, "fp16": FP16, "fp32": FP32}
 CONV_AUTO, CONV_SIMT, CONV_TC_GATHER, CONV_TC_TMA = 0, 1, 2, 3
 OP_CONV, OP_MAXPOOL3S2, OP_AVGPOOL, OP_TAP = 0, 1, 2, 3
 MAX_PARTS = 64
+INPUT_NHWC8, INPUT_S2D_ROW4 = 0, 1
 
 
 class SemdiffOp(C.Structure):
@@ -26,7 +27,7 @@ class SemdiffOp(C.Structure):
 # name -> (restype, argtypes); every symbol include/semdiff_b200.h declares
 _P, _I, _L = C.c_void_p, C.c_int32, C.c_int64
 SIGNATURES = {
-    "semdiff_plan_create": (_I, [C.POINTER(SemdiffOp), _I, _I, _I, C.POINTER(_P)]),
+    "semdiff_plan_create": (_I, [C.POINTER(SemdiffOp), _I, _I, _I, _I, C.POINTER(_P)]),
     "semdiff_plan_destroy": (_I, [_P]),
     "semdiff_plan_set_conv_impl": (_I, [_P, _I]),
     "semdiff_workspace_bytes": (_L, [_P, _I, _I, _I]),
@@ -34,7 +35,7 @@ SIGNATURES = {
     "semdiff_plan_set_profiling": (_I, [_P, _I]),
     "semdiff_plan_get_profile": (_I, [_P, C.POINTER(C.c_float), C.POINTER(_I), _I, _I]),
     "semdiff_plan_last_launches": (_L, [_P]),
-    "semdiff_pack_nhwc": (_I, [_P, _P, _I, _I, _I, _P, _I, _P]),
+    "semdiff_pack_input": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P]),
     "semdiff_conv2d": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "semdiff_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

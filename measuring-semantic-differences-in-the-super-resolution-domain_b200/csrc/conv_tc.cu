@@ -413,10 +413,12 @@ static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, con
   return 0;
 }
 
-static int pick_block_n(int cout, bool has_res, int m_tiles, int sms) {
+static int pick_block_n(int cout, bool has_res, int num_kb, int m_tiles, int sms) {
   if (cout % 128 != 0) return cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0);
   if (has_res || cout % 256 != 0) return 128;
-  // 256-wide tiles halve the A re-reads and relieve shared-memory bandwidth, but need enough tiles to fill the SMs
+  // 256-wide tiles raise the FLOP per operand byte fetched from L2 (compute-bound convs: K >= 512) but stage their
+  // output through a single smem slot; short-K convs are store-bound and want the 3-slot ring of the 128-wide tile
+  if (num_kb < 8) return 128;
   return (int64_t)m_tiles * (cout / 256) >= sms ? 256 : 128;
 }
 
@@ -499,7 +501,8 @@ int conv_tc_prepare(ConvTcLaunch* L, const void* in, const void* w, const float*
   const int a_mode = a_mode_for(s, use_tma ? SEMDIFF_CONV_TC_TMA : SEMDIFF_CONV_TC_GATHER);
   p.M = (int)s.M();
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  const int block_n = pick_block_n(s.cout, res != nullptr, p.m_tiles, num_sms());
+  p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K;
+  const int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
   if (block_n == 0) { set_error("conv_tc: cout %d not a multiple of 32", s.cout); return SEMDIFF_ERR_UNSUPPORTED; }
   p.in = in; p.bias = bias; p.has_res = res != nullptr;
   p.H = s.H; p.W = s.W; p.Cin = s.cin; p.OH = s.OH(); p.OW = s.OW(); p.Cout = s.cout;

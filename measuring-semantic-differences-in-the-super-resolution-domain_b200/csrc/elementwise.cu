@@ -25,6 +25,56 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ gt,
   }
 }
 
+// Stem layout (SEMDIFF_INPUT_S2D_ROW4) for 7x7 stride-2 pad-3 stems: the conv becomes a 4x1 stride-1 conv over
+//   X2[img, i, q, j*16 + (dy*2+dx)*3 + ci] = x[img, ci, 2*(i-2)+dy, 2*(q-2+j)+dx]   (0 outside the image, channels
+//   12..15 of every 16 are 0), i in [0, H/2+3), q in [0, W/2), j in [0, 4)
+// i.e. a 2x2 space-to-depth of the image with the four horizontally adjacent s2d pixels of each output column
+// laid side by side (64 "channels" = one 128-byte row), so the implicit GEMM runs with K = 4 x 64 instead of the
+// 49 x 8 a channel-padded 7x7 window would need.  One thread per (img, i, q, j): 6 float2 reads, 32 bytes written.
+template <typename T>
+__global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ gt, const float* __restrict__ sr,
+                                                       int n_pairs, int H, int W, T* __restrict__ out) {
+  const int H2 = H / 2 + 3, W2 = W / 2;
+  const int64_t total = (int64_t)2 * n_pairs * H2 * W2 * 4;
+  const int64_t plane = (int64_t)H * W;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t & 3);
+    int64_t r = t >> 2;
+    const int q = (int)(r % W2); r /= W2;
+    const int i = (int)(r % H2);
+    const int img = (int)(r / H2);
+    const float* src = img < n_pairs ? gt + (int64_t)img * 3 * plane : sr + (int64_t)(img - n_pairs) * 3 * plane;
+    const int y0 = 2 * (i - 2), x0 = 2 * (q - 2 + j);
+    float f[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) f[k] = 0.f;
+    if (x0 >= 0 && x0 < W) {
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const int y = y0 + dy;
+        if (y < 0 || y >= H) continue;
+#pragma unroll
+        for (int ci = 0; ci < 3; ++ci) {
+          const float2 v = __ldg(reinterpret_cast<const float2*>(src + ci * plane + (int64_t)y * W + x0));
+          f[(dy * 2 + 0) * 3 + ci] = v.x;
+          f[(dy * 2 + 1) * 3 + ci] = v.y;
+        }
+      }
+    }
+    T* dst = out + t * 16;
+    if constexpr (sizeof(T) == 2) {
+      float lo[8], hi[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { lo[k] = f[k]; hi[k] = f[8 + k]; }
+      reinterpret_cast<uint4*>(dst)[0] = pack8<T>(lo);
+      reinterpret_cast<uint4*>(dst)[1] = pack8<T>(hi);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) reinterpret_cast<float4*>(dst)[k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+    }
+  }
+}
+
 template <typename T> struct Vec8 {
   static __device__ __forceinline__ void load(const T* p, float (&f)[8]) {
     if constexpr (sizeof(T) == 2) {
@@ -107,23 +157,31 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ in, 
 
 static int grid_for(int64_t total, int block) {
   int64_t g = (total + block - 1) / block;
-  const int64_t cap = 148 * 16;  // a few waves of 256-thread CTAs over 148 SMs; grid-stride covers the rest
+  const int64_t cap = 148 * 32;  // a few waves of 256-thread CTAs over 148 SMs; grid-stride covers the rest
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
 template <typename T>
-static int pack_t(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, cudaStream_t st) {
-  const int64_t total = (int64_t)2 * n_pairs * H * W;
-  pack_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, H * W, (T*)out);
+static int pack_t(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int layout, cudaStream_t st) {
+  if (layout == SEMDIFF_INPUT_S2D_ROW4) {
+    const int64_t total = (int64_t)2 * n_pairs * (H / 2 + 3) * (W / 2) * 4;
+    pack_s2d_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, H, W, (T*)out);
+  } else {
+    const int64_t total = (int64_t)2 * n_pairs * H * W;
+    pack_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, H * W, (T*)out);
+  }
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int precision, cudaStream_t st) {
+int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int precision, int layout,
+                cudaStream_t st) {
   if (n_pairs <= 0 || H <= 0 || W <= 0) { set_error("pack: bad shape"); return SEMDIFF_ERR_ARG; }
+  if (layout == SEMDIFF_INPUT_S2D_ROW4 && ((H | W) & 1)) { set_error("pack: the s2d stem layout needs even H and W"); return SEMDIFF_ERR_ARG; }
+  if (layout != SEMDIFF_INPUT_NHWC8 && layout != SEMDIFF_INPUT_S2D_ROW4) { set_error("pack: bad layout %d", layout); return SEMDIFF_ERR_ARG; }
   switch (precision) {
-    case SEMDIFF_BF16: return pack_t<__nv_bfloat16>(gt, sr, n_pairs, H, W, out, st);
-    case SEMDIFF_FP16: return pack_t<__half>(gt, sr, n_pairs, H, W, out, st);
-    case SEMDIFF_FP32: return pack_t<float>(gt, sr, n_pairs, H, W, out, st);
+    case SEMDIFF_BF16: return pack_t<__nv_bfloat16>(gt, sr, n_pairs, H, W, out, layout, st);
+    case SEMDIFF_FP16: return pack_t<__half>(gt, sr, n_pairs, H, W, out, layout, st);
+    case SEMDIFF_FP32: return pack_t<float>(gt, sr, n_pairs, H, W, out, layout, st);
   }
   set_error("pack: bad precision %d", precision);
   return SEMDIFF_ERR_ARG;

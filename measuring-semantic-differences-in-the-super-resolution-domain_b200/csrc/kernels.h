@@ -18,7 +18,7 @@ struct ConvShape {
 inline size_t elem_bytes(int precision) { return precision == SEMDIFF_FP32 ? 4 : 2; }
 
 // each returns 0 / negative error code; all asynchronous on `stream`
-int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int precision,
+int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int precision, int layout,
                 cudaStream_t stream);
 int launch_maxpool3x3s2(const void* in, void* out, int n_img, int H, int W, int c, int precision, cudaStream_t stream);
 int launch_avgpool(const void* in, void* out, int n_img, int H, int W, int c, int window, int precision,

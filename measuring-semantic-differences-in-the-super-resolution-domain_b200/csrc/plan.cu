@@ -40,7 +40,7 @@ using namespace semdiff;
 
 struct semdiff_plan {
   std::vector<semdiff_op> ops;
-  int n_bufs = 0, precision = 0, n_taps = 0, conv_impl = SEMDIFF_CONV_AUTO;
+  int n_bufs = 0, precision = 0, n_taps = 0, conv_impl = SEMDIFF_CONV_AUTO, input_layout = SEMDIFF_INPUT_NHWC8;
   std::vector<int> tap_c, tap_off;  // channels and head_w offset per tap
   int chan_total = 0;
   std::map<std::tuple<int, int, int>, ShapePlan> shapes;  // key: (pairs in micro-batch, H, W)
@@ -59,8 +59,13 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
   std::vector<BufShape> cur(P->n_bufs);
   std::vector<int64_t> buf_elems(P->n_bufs, 0);
   const int64_t n_img = 2 * (int64_t)pairs;
-  cur[0] = BufShape{H, W, 8};
-  buf_elems[0] = n_img * H * W * 8;
+  if (P->input_layout == SEMDIFF_INPUT_S2D_ROW4) {
+    if ((H | W) & 1) { set_error("the s2d stem layout needs even H and W (got %dx%d)", H, W); return SEMDIFF_ERR_ARG; }
+    cur[0] = BufShape{H / 2 + 3, W / 2, 64};
+  } else {
+    cur[0] = BufShape{H, W, 8};
+  }
+  buf_elems[0] = n_img * cur[0].h * cur[0].w * cur[0].c;
   S->op_src.assign(n_ops, BufShape());
   S->op_dst.assign(n_ops, BufShape());
   for (int i = 0; i < n_ops; ++i) {
@@ -165,10 +170,13 @@ extern "C" {
 const char* semdiff_last_error(void) { return g_err; }
 const char* semdiff_version(void) { return "semdiff_b200 0.1 sm_100a"; }
 
-int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision, semdiff_plan** out) {
+int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision, int32_t input_layout,
+                        semdiff_plan** out) {
   if (ops == nullptr || out == nullptr || n_ops <= 0 || n_bufs < 2) { set_error("plan_create: bad arguments"); return SEMDIFF_ERR_ARG; }
   if (precision < SEMDIFF_BF16 || precision > SEMDIFF_FP32) { set_error("plan_create: bad precision %d", precision); return SEMDIFF_ERR_ARG; }
+  if (input_layout != SEMDIFF_INPUT_NHWC8 && input_layout != SEMDIFF_INPUT_S2D_ROW4) { set_error("plan_create: bad input layout %d", input_layout); return SEMDIFF_ERR_ARG; }
   semdiff_plan* P = new semdiff_plan();
+  P->input_layout = input_layout;
   P->ops.assign(ops, ops + n_ops);
   P->n_bufs = n_bufs;
   P->precision = precision;
@@ -283,7 +291,8 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
     int tap_parts[16], tap_hw[16];
     {
       ProfScope ps(P, n_ops + 0, st);
-      int rc = launch_pack(gt + p0 * img_elems, sr + p0 * img_elems, cur, H, W, ws + S.buf_offset[0], P->precision, st);
+      int rc = launch_pack(gt + p0 * img_elems, sr + p0 * img_elems, cur, H, W, ws + S.buf_offset[0], P->precision,
+                           P->input_layout, st);
       if (rc != 0) return rc;
       P->last_launches++;
     }
@@ -331,9 +340,9 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
   return 0;
 }
 
-int semdiff_pack_nhwc(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
-                      int32_t precision, semdiff_stream_t st) {
-  return launch_pack(gt, sr, n_pairs, H, W, out, precision, reinterpret_cast<cudaStream_t>(st));
+int semdiff_pack_input(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
+                       int32_t precision, int32_t layout, semdiff_stream_t st) {
+  return launch_pack(gt, sr, n_pairs, H, W, out, precision, layout, reinterpret_cast<cudaStream_t>(st));
 }
 
 int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out, int32_t n_img,

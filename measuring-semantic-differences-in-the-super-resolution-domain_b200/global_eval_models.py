@@ -32,11 +32,12 @@ from .processor import make_processor
 class _Plan:
     """Device-resident folded weights + the native plan handle.  Rebuilt when trunk weights change."""
 
-    def __init__(self, clip: nn.Module, family: str, depth: int, precision: str, device: torch.device):
+    def __init__(self, clip: nn.Module, family: str, depth: int, precision: str, device: torch.device,
+                 s2d_stem: bool = True):
         self.lib = _lib.load()
         self.precision = _lib.PRECISIONS[precision]
         dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[precision]
-        self.program = trunks.LOWER[family](clip, depth)
+        self.program = trunks.LOWER[family](clip, depth, s2d_stem)
         ops = self.program.ops
         self._keep = []
         arr = (_lib.SemdiffOp * len(ops))()
@@ -50,8 +51,8 @@ class _Plan:
             arr[i] = _lib.SemdiffOp(op["kind"], op["src"], op["dst"], op["res"], op["cin"], op["cout"], op["kh"],
                                     op["kw"], op["stride"], op["pad"], op["relu"], op["tap"], w_ptr, b_ptr)
         handle = C.c_void_p()
-        _lib.check(self.lib.semdiff_plan_create(arr, len(ops), self.program.n_bufs, self.precision, C.byref(handle)),
-                   "semdiff_plan_create")
+        _lib.check(self.lib.semdiff_plan_create(arr, len(ops), self.program.n_bufs, self.precision,
+                                                self.program.input_layout, C.byref(handle)), "semdiff_plan_create")
         self.handle = handle
         self.n_ops = len(ops)
         self.device = device
@@ -140,7 +141,7 @@ class _B200Scorer(nn.Module):
         self.w_layers.to(dev)
         self.precision, self.microbatch, self.normalize = precision, microbatch, normalize
         self._device = dev
-        self._plan: _Plan | None = None
+        self._plan: dict[bool, _Plan] = {}
         self._tap_offsets = []
         off = 0
         for m in self.w_layers:
@@ -175,25 +176,27 @@ class _B200Scorer(nn.Module):
         return self
 
     def _apply(self, fn, *args, **kwargs):
-        self._plan = None
+        self._plan = {}
         return super()._apply(fn, *args, **kwargs)
 
     def load_state_dict(self, *args, **kwargs):
-        self._plan = None
+        self._plan = {}
         return super().load_state_dict(*args, **kwargs)
 
     def refresh(self):
         """Re-fold the trunk after its parameters were modified in place."""
-        self._plan = None
+        self._plan = {}
 
     # ---- native call -----------------------------------------------------------------------
-    def plan(self) -> _Plan:
-        if self._plan is None:
+    def plan(self, even_size: bool = True) -> _Plan:
+        """The native plan; images with an odd height or width use a second plan whose stem is the generic
+        channel-padded conv (the space-to-depth stem layout needs even sizes)."""
+        if even_size not in self._plan:
             dev = next(self.w_layers.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("the module was moved off the GPU; the B200 scorer has no CPU fallback")
-            self._plan = _Plan(self.clip, self.family, self.depth, self.precision, dev)
-        return self._plan
+            self._plan[even_size] = _Plan(self.clip, self.family, self.depth, self.precision, dev, s2d_stem=even_size)
+        return self._plan[even_size]
 
     def default_microbatch(self, H: int, W: int) -> int:
         if self.microbatch:
@@ -203,8 +206,8 @@ class _B200Scorer(nn.Module):
         return max(1, min(64, (64 << 20) // max(per_pair, 1)))
 
     def _run(self, a, b, head_w, head_b, want_grad: bool = False):
-        plan = self.plan()
         n, _, H, W = a.shape
+        plan = self.plan(H % 2 == 0 and W % 2 == 0)
         a = a.detach().contiguous().float()
         b = b.detach().contiguous().float()
         hw_, hb_ = head_w.detach().contiguous(), head_b.detach().contiguous()

@@ -162,13 +162,30 @@ class Program:
     def __init__(self):
         self.ops: list[dict] = []
         self.n_bufs = 0
-        self.flops_per_image_224 = 0
+        self.input_layout = _lib.INPUT_NHWC8
 
     def conv(self, conv, bn, src, dst, res=-1, relu=True, cin_pad=None):
         w, b = fold_conv_bn(conv, bn, cin_pad)
         self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=res, cin=w.shape[3], cout=w.shape[0],
                              kh=w.shape[1], kw=w.shape[2], stride=conv.stride[0], pad=conv.padding[0],
-                             relu=int(relu), tap=-1, w=w, b=b, true_cin=conv.in_channels))
+                             relu=int(relu), tap=-1, w=w, b=b,
+                             alg_k=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1]))
+
+    def stem7_s2d(self, conv, bn, src, dst):
+        """7x7 stride-2 pad-3 stem as a 4x1 stride-1 conv over the SEMDIFF_INPUT_S2D_ROW4 buffer (csrc/elementwise.cu):
+        tap ky -> (row r = (ky+1)//2, sub-row dy = (ky+1)%2), kx -> (window pixel j = (kx+1)//2, dx = (kx+1)%2),
+        channel slot j*16 + (dy*2+dx)*3 + ci.  K = 4*64 = 256 instead of 49*8 = 392 for a channel-padded 7x7."""
+        w, b = fold_conv_bn(conv, bn)                      # [Cout, 7, 7, 3]
+        w2 = torch.zeros(w.shape[0], 4, 1, 64, dtype=w.dtype)
+        for ky in range(7):
+            r, dy = (ky + 1) // 2, (ky + 1) % 2
+            for kx in range(7):
+                j, dx = (kx + 1) // 2, (kx + 1) % 2
+                base = j * 16 + (dy * 2 + dx) * 3
+                w2[:, r, 0, base:base + 3] = w[:, ky, kx, :]
+        self.input_layout = _lib.INPUT_S2D_ROW4
+        self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=-1, cin=64, cout=w.shape[0], kh=4, kw=1, stride=1,
+                             pad=0, relu=1, tap=-1, w=w2, b=b, alg_k=147))
 
     def pool(self, kind, src, dst, window):
         self.ops.append(dict(kind=kind, src=src, dst=dst, res=-1, cin=0, cout=0, kh=window, kw=window, stride=window,
@@ -179,12 +196,17 @@ class Program:
                              relu=0, tap=j, w=None, b=None))
 
 
-def lower_resnet50(clip: nn.Module, depth: int) -> Program:
-    """timm resnet50; taps = layer{s}.2.act3 for s in range(4-depth, 5)  (global_eval_models.py:701)."""
+def lower_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Program:
+    """timm resnet50; taps = layer{s}.2.act3 for s in range(4-depth, 5)  (global_eval_models.py:701).
+    s2d_stem=False keeps the stem as a channel-padded 7x7 conv (needed for odd image sizes)."""
     P = Program()
     IN, A, B, T1, T2, DS = range(6)
     P.n_bufs = 6
-    P.conv(clip.conv1, clip.bn1, IN, T1, cin_pad=8)
+    c1 = clip.conv1
+    if s2d_stem and c1.kernel_size == (7, 7) and c1.stride == (2, 2) and c1.padding == (3, 3) and c1.in_channels == 3:
+        P.stem7_s2d(c1, clip.bn1, IN, T1)
+    else:
+        P.conv(c1, clip.bn1, IN, T1, cin_pad=8)
     P.pool(_lib.OP_MAXPOOL3S2, T1, A, 3)
     x = A
     for li in range(1, 5):
@@ -206,7 +228,7 @@ def lower_resnet50(clip: nn.Module, depth: int) -> Program:
     return P
 
 
-def lower_clip_resnet50(clip: nn.Module, depth: int) -> Program:
+def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Program:
     """timm resnet50_clip.openai; taps = stages.{s}.2.act for s in range(3-depth, 4)  (global_eval_models.py:327)."""
     P = Program()
     IN, A, B, T1, T2, T3, D0, DS = range(8)
@@ -248,14 +270,14 @@ LOWER = {"resnet50": lower_resnet50, "resnet50_clip.openai": lower_clip_resnet50
 
 def conv_flops(program: Program, H: int, W: int) -> int:
     """Algorithmic FLOPs (2*MAC, unpadded Cin) of the conv ops for ONE HxW image."""
-    shapes = {0: (H, W)}
+    shapes = {0: (H // 2 + 3, W // 2) if program.input_layout == _lib.INPUT_S2D_ROW4 else (H, W)}
     total = 0
     for op in program.ops:
         h, w = shapes[op["src"]]
         if op["kind"] == _lib.OP_CONV:
             oh = (h + 2 * op["pad"] - op["kh"]) // op["stride"] + 1
             ow = (w + 2 * op["pad"] - op["kw"]) // op["stride"] + 1
-            total += 2 * oh * ow * op["cout"] * op["kh"] * op["kw"] * op["true_cin"]
+            total += 2 * oh * ow * op["cout"] * op["alg_k"]
             shapes[op["dst"]] = (oh, ow)
         elif op["kind"] == _lib.OP_MAXPOOL3S2:
             shapes[op["dst"]] = ((h - 1) // 2 + 1, (w - 1) // 2 + 1)

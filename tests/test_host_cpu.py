@@ -63,6 +63,9 @@ def test_fold_conv_bn_matches_torch():
 @pytest.mark.parametrize("name,convs,gflop", [("resnet50", 53, 8.174272512), ("resnet50_clip.openai", 55, 10.734452736)])
 def test_lowering(name, convs, gflop):
     tree = trunks.create_trunk(name)
+    generic = trunks.LOWER[name](tree, 3, False)
+    assert generic.input_layout == _lib.INPUT_NHWC8
+    assert abs(trunks.conv_flops(generic, 224, 224) / 1e9 - gflop) < 1e-9
     for depth in range(4):
         prog = trunks.LOWER[name](tree, depth)
         assert sum(op["kind"] == _lib.OP_CONV for op in prog.ops) == convs
@@ -85,7 +88,34 @@ def test_plan_api_rejects_bad_arguments_without_gpu():
     lib = _lib.load()
     import ctypes as C
     handle = C.c_void_p()
-    assert lib.semdiff_plan_create(None, 0, 0, 0, C.byref(handle)) == -1
+    assert lib.semdiff_plan_create(None, 0, 0, 0, 0, C.byref(handle)) == -1
     assert b"bad arguments" in lib.semdiff_last_error()
     assert lib.semdiff_distance_parts(56 * 56, 256) == 25 and lib.semdiff_distance_parts(49, 2048) == 4
     assert lib.semdiff_distance_parts(1, 8) == 1 and lib.semdiff_distance_parts(1024 * 1024, 256) == 64
+
+
+def test_s2d_stem_weights_reproduce_the_7x7_conv():
+    """The 4x1 conv over the space-to-depth row-window layout (pack_s2d_kernel) equals the 7x7/2 pad-3 conv."""
+    torch.manual_seed(0)
+    tree = trunks.create_trunk("resnet50")
+    with torch.no_grad():
+        tree.bn1.running_mean.normal_(); tree.bn1.running_var.uniform_(0.5, 2.0); tree.bn1.bias.normal_()
+    prog = trunks.lower_resnet50(tree, 0)
+    assert prog.input_layout == _lib.INPUT_S2D_ROW4
+    op = prog.ops[0]
+    assert (op["kh"], op["kw"], op["cin"], op["stride"], op["pad"], op["alg_k"]) == (4, 1, 64, 1, 0, 147)
+    H, W = 12, 16
+    x = torch.randn(2, 3, H, W, dtype=torch.double)
+    # the layout the pack kernel writes: X2[n, i, q, j*16 + (dy*2+dx)*3 + ci] = x[n, ci, 2(i-2)+dy, 2(q-2+j)+dx]
+    X2 = torch.zeros(2, H // 2 + 3, W // 2, 64, dtype=torch.double)
+    for i in range(H // 2 + 3):
+        for q in range(W // 2):
+            for j in range(4):
+                for dy in range(2):
+                    for dx in range(2):
+                        y, xx = 2 * (i - 2) + dy, 2 * (q - 2 + j) + dx
+                        if 0 <= y < H and 0 <= xx < W:
+                            X2[:, i, q, j * 16 + (dy * 2 + dx) * 3: j * 16 + (dy * 2 + dx) * 3 + 3] = x[:, :, y, xx]
+    got = torch.nn.functional.conv2d(X2.permute(0, 3, 1, 2), op["w"].permute(0, 3, 1, 2), op["b"])
+    ref = tree.bn1.double().eval()(tree.conv1.double()(x))
+    assert got.shape == ref.shape and torch.allclose(got, ref, rtol=1e-10, atol=1e-10)

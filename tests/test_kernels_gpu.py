@@ -18,10 +18,34 @@ def test_pack(precision):
     gt = torch.randn(3, 3, 20, 28, device=DEV, generator=g)
     sr = torch.randn(3, 3, 20, 28, device=DEV, generator=g)
     out = torch.full((6, 20, 28, 8), 7.0, dtype=DT[precision], device=DEV)
-    _lib.check(lib().semdiff_pack_nhwc(gt.data_ptr(), sr.data_ptr(), 3, 20, 28, out.data_ptr(), _lib.PRECISIONS[precision], sp()), "pack")
+    _lib.check(lib().semdiff_pack_input(gt.data_ptr(), sr.data_ptr(), 3, 20, 28, out.data_ptr(), _lib.PRECISIONS[precision],
+                                        _lib.INPUT_NHWC8, sp()), "pack")
     ref = torch.cat([gt, sr]).permute(0, 2, 3, 1).to(DT[precision])
     assert torch.equal(out[..., :3], ref)
     assert torch.count_nonzero(out[..., 3:]) == 0
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_pack_s2d_row_window(precision):
+    H, W = 12, 16
+    g = torch.Generator(device=DEV).manual_seed(0)
+    gt = torch.randn(2, 3, H, W, device=DEV, generator=g)
+    sr = torch.randn(2, 3, H, W, device=DEV, generator=g)
+    out = torch.full((4, H // 2 + 3, W // 2, 64), 7.0, dtype=DT[precision], device=DEV)
+    _lib.check(lib().semdiff_pack_input(gt.data_ptr(), sr.data_ptr(), 2, H, W, out.data_ptr(), _lib.PRECISIONS[precision],
+                                        _lib.INPUT_S2D_ROW4, sp()), "pack")
+    x = torch.cat([gt, sr])
+    ref = torch.zeros(4, H // 2 + 3, W // 2, 64, device=DEV)
+    for i in range(H // 2 + 3):
+        for q in range(W // 2):
+            for j in range(4):
+                for dy in range(2):
+                    for dx in range(2):
+                        y, xx = 2 * (i - 2) + dy, 2 * (q - 2 + j) + dx
+                        if 0 <= y < H and 0 <= xx < W:
+                            c = j * 16 + (dy * 2 + dx) * 3
+                            ref[:, i, q, c:c + 3] = x[:, :, y, xx]
+    assert torch.equal(out, ref.to(DT[precision]))
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])

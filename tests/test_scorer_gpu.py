@@ -166,3 +166,20 @@ def test_head_gradients():
     for m, r in zip(model.w_layers, ref_model.w_layers):
         assert torch.allclose(m.weight.grad.cpu(), r.weight.grad, rtol=1e-3, atol=1e-6)
         assert torch.allclose(m.bias.grad.cpu(), r.bias.grad, rtol=1e-3, atol=1e-6)
+
+
+@pytest.mark.parametrize("size", [(225, 223), (256, 320)])
+def test_other_image_sizes_fp32(size):
+    """Fully convolutional like the reference: non-224 sizes; odd sizes take the generic (non space-to-depth) stem."""
+    oracle, model = oracle_and_module("resnet50", 3, "fp32")
+    g = torch.Generator().manual_seed(3)
+    gt = torch.randn(2, 3, *size, generator=g)
+    sr = gt + 0.2 * torch.randn(2, 3, *size, generator=g)
+    ref = oracle(gt, sr)
+    with torch.no_grad():
+        got = model(gt.cuda(), sr.cuda()).cpu()
+    assert rel_err(got, ref) < 1e-5, (got, ref)
+    _, m16 = oracle_and_module("resnet50", 3, "bf16")
+    with torch.no_grad():
+        got16 = m16(gt.cuda(), sr.cuda()).cpu()
+    assert rel_err(got16, ref) < 6e-2
