@@ -86,8 +86,11 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  // one lane per warp, elected once: ptxas then knows that the single-thread roles below (TMA / tcgen05 issue) are
+  // single-lane and emits the uniform-datapath instructions directly instead of an elect-and-retry loop per instruction
+  const bool leader = elect_one();
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && leader) {
     if (kAMode != A_GATHER) tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmC);
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (leader) {
       int stage = 0, phase = 0;
       const int kb_per_tap = p.Cin >> 6;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -146,29 +149,31 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(Elem<T>::kUmmaFormat, BLOCK_M, BLOCK_N);
-      int stage = 0, phase = 0, local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
-        const int acc = local & 1, acc_phase = (local >> 1) & 1;
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+    // ===================== MMA issuer (whole warp waits, the elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_f16(Elem<T>::kUmmaFormat, BLOCK_M, BLOCK_N);
+    // descriptors differ between stages / K steps only in the 14-bit start-address field: precompute and add
+    const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(smem_a));
+    const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(smem_b));
+    int stage = 0, phase = 0, local = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int acc = local & 1, acc_phase = (local >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * A_STAGE_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES);
+        if (leader) {
+          const uint64_t a_desc = a_desc0 + (uint64_t)((stage * A_STAGE_BYTES) >> 4);
+          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * Cfg::B_STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            umma_f16_ss(tmem_d, umma_smem_desc_sw128(a_addr + k * 32), umma_smem_desc_sw128(b_addr + k * 32), idesc,
-                        (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp < 6) {
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
     constexpr int ROW_BYTES = Cfg::BOX_COLS * 2;
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
-    const bool store_thread = (warp == 2 && lane == 0);
+    const bool store_thread = (warp == 2 && leader);
     int local = 0, gc = 0;  // gc: running column-group counter of this CTA (ring position)
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -257,7 +262,7 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
     if (store_thread) bulk_wait<0>();  // smem must stay valid until the last store has completed
   } else if (warp == (kAMode == A_GATHER ? 10 : 6)) {
     // ===================== residual loader =====================
-    if (lane == 0 && p.has_res) {
+    if (leader && p.has_res) {
       int gc = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
