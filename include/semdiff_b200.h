@@ -63,6 +63,9 @@ typedef struct semdiff_op {
   int32_t pad;
   int32_t relu;      /* apply ReLU in the epilogue */
   int32_t tap;       /* for TAP: index j of w_layers[j] (:336) this activation feeds */
+  int32_t src2;      /* CONV: second input buffer read through a fused 1x1 conv (projection shortcut), or -1 */
+  int32_t cin2;      /* channels of src2; weight rows are [kh*kw*cin | cin2] */
+  int32_t stride2;   /* spatial stride of the fused 1x1 conv over src2 */
   const void* weight; /* device, [cout][kh][kw][cin] in the plan's precision */
   const float* bias;  /* device, [cout] fp32 (folded BN shift) */
 } semdiff_op;
@@ -107,11 +110,12 @@ int64_t semdiff_plan_last_launches(const semdiff_plan* plan);
 int semdiff_pack_input(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
                        int32_t precision, int32_t layout, semdiff_stream_t stream);
 
-/* out = act(conv(in, weight) + bias (+ residual)); NHWC; impl = SEMDIFF_CONV_* */
+/* out = act(conv(in, weight[:, :kh*kw*cin]) (+ conv1x1_stride2(in2, weight[:, kh*kw*cin:])) + bias (+ residual));
+ * NHWC; in2 may be NULL; impl = SEMDIFF_CONV_* */
 int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out,
                    int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw,
-                   int32_t stride, int32_t pad, int32_t relu, int32_t precision, int32_t impl,
-                   semdiff_stream_t stream);
+                   int32_t stride, int32_t pad, int32_t relu, const void* in2, int32_t H2, int32_t W2, int32_t cin2,
+                   int32_t stride2, int32_t precision, int32_t impl, semdiff_stream_t stream);
 
 int semdiff_maxpool3x3s2(const void* in, void* out, int32_t n_img, int32_t H, int32_t W, int32_t c,
                          int32_t precision, semdiff_stream_t stream);

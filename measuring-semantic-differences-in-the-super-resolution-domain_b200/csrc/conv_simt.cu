@@ -9,9 +9,10 @@ namespace semdiff {
 constexpr int TM = 64, TN = 64, TK = 16;
 
 template <typename T>
-__global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ in, const T* __restrict__ wgt,
-                                                        const float* __restrict__ bias, const T* __restrict__ res,
-                                                        T* __restrict__ out, ConvShape s, int OH, int OW, int M, int K) {
+__global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ in, const T* __restrict__ in2,
+                                                        const T* __restrict__ wgt, const float* __restrict__ bias,
+                                                        const T* __restrict__ res, T* __restrict__ out, ConvShape s,
+                                                        int OH, int OW, int M, int K, int K1) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN + 4];
   const int tid = threadIdx.x;
@@ -33,7 +34,12 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ in
     {
       float v[4] = {0.f, 0.f, 0.f, 0.f};
       const int k = k0 + lk;
-      if (row_ok && k < K) {
+      if (row_ok && k >= K1 && k < K) {
+        // fused second source: 1x1 conv, stride2, no padding
+        const T* p = in2 + (((int64_t)n * s.H2 + oh * s.stride2) * s.W2 + ow * s.stride2) * s.cin2 + (k - K1);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = Elem<T>::to_f(p[j]);
+      } else if (row_ok && k < K1) {
         const int tap = k / s.cin, c = k - tap * s.cin;
         const int r = tap / s.kw, q = tap - r * s.kw;
         const int ih = oh * s.stride - s.pad + r, iw = ow * s.stride - s.pad + q;
@@ -89,28 +95,26 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const T* __restrict__ in
 }
 
 template <typename T>
-static int conv_simt_t(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
-                       cudaStream_t st) {
+static int conv_simt_t(const ConvPtrs& q, const ConvShape& s, cudaStream_t st) {
   const int OH = s.OH(), OW = s.OW();
   const int64_t M = s.M();
   if (M > 0x7fffffffLL) { set_error("conv_simt: M too large"); return SEMDIFF_ERR_ARG; }
   dim3 grid((unsigned)((M + TM - 1) / TM), (unsigned)((s.cout + TN - 1) / TN));
-  conv_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)in, (const T*)w, bias, (const T*)res, (T*)out, s, OH, OW, (int)M,
-                                            s.K());
+  conv_simt_kernel<T><<<grid, 256, 0, st>>>((const T*)q.in, (const T*)q.in2, (const T*)q.w, q.bias, (const T*)q.res,
+                                            (T*)q.out, s, OH, OW, (int)M, s.K(), s.K1());
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
-int launch_conv_simt(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
-                     int precision, cudaStream_t st) {
-  if (s.cin % 4 != 0 || s.n_img <= 0 || s.OH() <= 0 || s.OW() <= 0) {
+int launch_conv_simt(const ConvPtrs& q, const ConvShape& s, int precision, cudaStream_t st) {
+  if (s.cin % 4 != 0 || s.cin2 % 4 != 0 || s.n_img <= 0 || s.OH() <= 0 || s.OW() <= 0) {
     set_error("conv_simt: need cin %% 4 == 0 and a non-empty output (cin=%d)", s.cin);
     return SEMDIFF_ERR_ARG;
   }
   switch (precision) {
-    case SEMDIFF_BF16: return conv_simt_t<__nv_bfloat16>(in, w, bias, res, out, s, st);
-    case SEMDIFF_FP16: return conv_simt_t<__half>(in, w, bias, res, out, s, st);
-    case SEMDIFF_FP32: return conv_simt_t<float>(in, w, bias, res, out, s, st);
+    case SEMDIFF_BF16: return conv_simt_t<__nv_bfloat16>(q, s, st);
+    case SEMDIFF_FP16: return conv_simt_t<__half>(q, s, st);
+    case SEMDIFF_FP32: return conv_simt_t<float>(q, s, st);
   }
   set_error("conv_simt: bad precision %d", precision);
   return SEMDIFF_ERR_ARG;

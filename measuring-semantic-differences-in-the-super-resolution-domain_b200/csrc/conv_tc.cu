@@ -51,6 +51,7 @@ template <int BLOCK_N> struct TcCfg {
 
 struct alignas(64) ConvTcParams {
   CUtensorMap tmA;  // activations: [M, Cin] tiled (A_TMA) or NHWC im2col (A_IM2COL)
+  CUtensorMap tmA2; // fused second source (1x1 conv): [M, Cin2] tiled when stride2 == 1, else NHWC im2col
   CUtensorMap tmB;  // weights as [Cout, K]
   CUtensorMap tmC;  // output as [M, Cout]
   CUtensorMap tmR;  // residual as [M, Cout]
@@ -58,8 +59,9 @@ struct alignas(64) ConvTcParams {
   const float* bias;
   int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, relu, has_res;
   int M, num_kb, m_tiles, n_tiles, cpt, taps;
+  int num_kb1, a2_im2col, stride2;  // k-blocks [num_kb1, num_kb) come from the second source
 };
-static_assert(sizeof(ConvTcParams) <= 768, "ConvTcLaunch::params too small");
+static_assert(sizeof(ConvTcParams) <= 896, "ConvTcLaunch::params too small");
 
 // 16-byte chunk position inside a swizzled row of ROW_BYTES (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B)
 template <int ROW_BYTES> __device__ __forceinline__ uint32_t swz_chunk(uint32_t chunk, uint32_t row) {
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
 
   if (warp == 0 && leader) {
     if (kAMode != A_GATHER) tma_prefetch_desc(&p.tmA);
+    if (p.num_kb1 < p.num_kb) tma_prefetch_desc(&p.tmA2);
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmC);
     if (p.has_res) tma_prefetch_desc(&p.tmR);
@@ -122,20 +125,28 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
       const int kb_per_tap = p.Cin >> 6;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-        int n = 0, h0 = 0, w0 = 0;
-        if (kAMode == A_IM2COL) {
+        int n = 0, h0 = 0, w0 = 0, h2 = 0, w2 = 0;
+        if (kAMode == A_IM2COL || p.a2_im2col) {
           const int gm = m_tile * BLOCK_M;
           n = gm / (p.OH * p.OW);
           const int r = gm - n * p.OH * p.OW;
           const int oh = r / p.OW, ow = r - oh * p.OW;
           h0 = oh * p.stride - p.pad;
           w0 = ow * p.stride - p.pad;
+          h2 = oh * p.stride2;
+          w2 = ow * p.stride2;
         }
         int tap = 0, cb = 0;  // filter tap and 64-channel block of the current k-block (im2col)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_STAGE_BYTES + (kAMode != A_GATHER ? A_STAGE_BYTES : 0));
-          if (kAMode == A_TMA) {
+          if (kb >= p.num_kb1) {
+            const int kb2 = kb - p.num_kb1;  // fused 1x1 conv over the second activation tensor
+            if (p.a2_im2col)
+              tma_load_im2col_4d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb2 * BLOCK_K, w2, h2, n, 0, 0);
+            else
+              tma_load_2d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb2 * BLOCK_K, m_tile * BLOCK_M);
+          } else if (kAMode == A_TMA) {
             tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
           } else if (kAMode == A_IM2COL) {
             const int r = tap / p.KW, s = tap - r * p.KW;
@@ -394,7 +405,9 @@ static int make_tmap_2d(CUtensorMap* m, const void* base, int precision, uint64_
 // NHWC activation as (C, W, H, N) in TMA im2col mode: one load = 128 consecutive output pixels x 64 channels of one
 // filter tap.  Corner arithmetic as in CUTLASS's fprop (conv/collective/detail.hpp compute_{lower,upper}_corner_whd):
 // lower = -pad, upper = pad - (k - 1); traversal stride = conv stride.
-static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, const ConvShape& s) {
+static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, const ConvShape& s_in, bool second) {
+  ConvShape s = s_in;
+  if (second) { s.H = s_in.H2; s.W = s_in.W2; s.cin = s_in.cin2; s.kh = s.kw = 1; s.stride = s_in.stride2; s.pad = 0; }
   static EncodeIm2colFn enc = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));
   if (enc == nullptr) { set_error("cuTensorMapEncodeIm2col entry point not found"); return SEMDIFF_ERR_CUDA; }
   const cuuint64_t dims[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.n_img};
@@ -441,6 +454,7 @@ bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma) {
   if (s.cin > 64 && s.cin % 64 != 0) return false;
   if (s.cin < 64 && 64 % s.cin != 0) return false;
   if (use_tma && s.cin % 64 != 0) return false;
+  if (s.cin2 != 0 && (!use_tma || s.cin2 % 64 != 0 || s.K1() % 64 != 0)) return false;
   return s.M() > 0 && s.M() < (int64_t)1 << 31;
 }
 
@@ -493,8 +507,8 @@ static int launch_mode(const ConvTcParams& p, int block_n, int a_mode, cudaStrea
   return SEMDIFF_ERR_UNSUPPORTED;
 }
 
-int conv_tc_prepare(ConvTcLaunch* L, const void* in, const void* w, const float* bias, const void* res, void* out,
-                    const ConvShape& s, int precision, bool use_tma) {
+int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision, bool use_tma) {
+  const void* in = q.in; const void* w = q.w; const float* bias = q.bias; const void* res = q.res; void* out = q.out;
   if (!conv_tc_supported(s, precision, use_tma)) {
     set_error("conv_tc: unsupported shape cin=%d cout=%d k=%dx%d stride=%d pad=%d tma=%d precision=%d", s.cin, s.cout,
               s.kh, s.kw, s.stride, s.pad, (int)use_tma, precision);
@@ -519,7 +533,16 @@ int conv_tc_prepare(ConvTcLaunch* L, const void* in, const void* w, const float*
   const uint32_t box_cols = block_n < 64 ? block_n : 64;
   int rc = make_tmap_2d(&p.tmB, w, precision, (uint64_t)s.cout, (uint64_t)s.K(), BLOCK_K, (uint32_t)block_n);
   if (rc == 0 && a_mode == A_TMA) rc = make_tmap_2d(&p.tmA, in, precision, (uint64_t)p.M, (uint64_t)s.cin, BLOCK_K, BLOCK_M);
-  if (rc == 0 && a_mode == A_IM2COL) rc = make_tmap_im2col(&p.tmA, in, precision, s);
+  if (rc == 0 && a_mode == A_IM2COL) rc = make_tmap_im2col(&p.tmA, in, precision, s, false);
+  p.num_kb1 = p.num_kb;
+  p.stride2 = 1;
+  if (rc == 0 && s.cin2 != 0) {
+    p.num_kb1 = s.K1() / BLOCK_K;
+    p.stride2 = s.stride2;
+    p.a2_im2col = s.stride2 != 1;
+    rc = p.a2_im2col ? make_tmap_im2col(&p.tmA2, q.in2, precision, s, true)
+                     : make_tmap_2d(&p.tmA2, q.in2, precision, (uint64_t)p.M, (uint64_t)s.cin2, BLOCK_K, BLOCK_M);
+  }
   if (rc == 0) rc = make_tmap_2d(&p.tmC, out, precision, (uint64_t)p.M, (uint64_t)s.cout, box_cols, BLOCK_M);
   if (rc == 0 && res != nullptr) rc = make_tmap_2d(&p.tmR, res, precision, (uint64_t)p.M, (uint64_t)s.cout, box_cols, BLOCK_M);
   if (rc != 0) return rc;
@@ -535,10 +558,9 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t st) {
   return launch_mode<__half>(p, L->block_n, L->a_mode, st);
 }
 
-int launch_conv_tc(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
-                   int precision, bool use_tma, cudaStream_t st) {
+int launch_conv_tc(const ConvPtrs& q, const ConvShape& s, int precision, bool use_tma, cudaStream_t st) {
   ConvTcLaunch L;
-  int rc = conv_tc_prepare(&L, in, w, bias, res, out, s, precision, use_tma);
+  int rc = conv_tc_prepare(&L, q, s, precision, use_tma);
   if (rc != 0) return rc;
   return conv_tc_launch(&L, st);
 }

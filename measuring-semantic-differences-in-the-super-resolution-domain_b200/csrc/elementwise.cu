@@ -1,4 +1,7 @@
 // Bandwidth-bound helpers of the trunk: image packing, max/avg pooling.  NHWC, 128-bit accesses.
+#include <algorithm>
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -35,15 +38,15 @@ template <typename T>
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ gt, const float* __restrict__ sr,
                                                        int n_pairs, int H, int W, T* __restrict__ out) {
   const int H2 = H / 2 + 3, W2 = W / 2;
-  const int64_t total = (int64_t)2 * n_pairs * H2 * W2 * 4;
-  const int64_t plane = (int64_t)H * W;
-  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int j = (int)(t & 3);
-    int64_t r = t >> 2;
-    const int q = (int)(r % W2); r /= W2;
-    const int i = (int)(r % H2);
-    const int img = (int)(r / H2);
-    const float* src = img < n_pairs ? gt + (int64_t)img * 3 * plane : sr + (int64_t)(img - n_pairs) * 3 * plane;
+  const int per_img = H2 * W2 * 4;
+  const int img = blockIdx.y;
+  const int plane = H * W;
+  const float* src = img < n_pairs ? gt + (int64_t)img * 3 * plane : sr + (int64_t)(img - n_pairs) * 3 * plane;
+  T* out_img = out + (int64_t)img * per_img * 16;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += gridDim.x * blockDim.x) {
+    const int j = t & 3;
+    const int r = t >> 2;
+    const int i = r / W2, q = r - i * W2;
     const int y0 = 2 * (i - 2), x0 = 2 * (q - 2 + j);
     float f[16];
 #pragma unroll
@@ -55,13 +58,13 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__
         if (y < 0 || y >= H) continue;
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(src + ci * plane + (int64_t)y * W + x0));
+          const float2 v = __ldg(reinterpret_cast<const float2*>(src + ci * plane + y * W + x0));
           f[(dy * 2 + 0) * 3 + ci] = v.x;
           f[(dy * 2 + 1) * 3 + ci] = v.y;
         }
       }
     }
-    T* dst = out + t * 16;
+    T* dst = out_img + (int64_t)t * 16;
     if constexpr (sizeof(T) == 2) {
       float lo[8], hi[8];
 #pragma unroll
@@ -95,36 +98,68 @@ template <typename T> struct Vec8 {
   }
 };
 
-// 3x3 stride-2 pad-1 max pool (torch MaxPool2d semantics: padding never wins)
+// 3x3 stride-2 pad-1 max pool (torch MaxPool2d semantics: padding never wins).  grid.y = image; 32-bit index math;
+// 16-bit types take the maximum on packed pairs without widening.
+template <typename T> __device__ __forceinline__ uint4 max8(const uint4& a, const uint4& b) {
+  uint4 r;
+  if constexpr (sizeof(T) == 2) {
+    using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
+    const T2* pa = reinterpret_cast<const T2*>(&a);
+    const T2* pb = reinterpret_cast<const T2*>(&b);
+    T2* pr = reinterpret_cast<T2*>(&r);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) pr[k] = __hmax2(pa[k], pb[k]);
+  }
+  return r;
+}
 template <typename T>
-__global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int H,
-                                                      int W, int C, int OH, int OW) {
+__global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
+                                                      int OH, int OW) {
   const int cv = C / 8;
-  const int64_t total = (int64_t)n_img * OH * OW * cv;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c8 = (int)(i % cv);
-    int64_t p = i / cv;
-    const int ow = (int)(p % OW); p /= OW;
-    const int oh = (int)(p % OH);
-    const int n = (int)(p / OH);
-    float m[8];
+  const int per_img = OH * OW * cv;
+  const T* img_in = in + (int64_t)blockIdx.y * H * W * C;
+  T* img_out = out + (int64_t)blockIdx.y * per_img * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
+    const int c8 = i % cv;
+    const int p = i / cv;
+    const int oh = p / OW, ow = p - oh * OW;
+    if constexpr (sizeof(T) == 2) {
+      uint4 m;
+      bool first = true;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+      for (int r = 0; r < 3; ++r) {
+        const int ih = oh * 2 - 1 + r;
+        if (ih < 0 || ih >= H) continue;
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int ih = oh * 2 - 1 + r;
-      if (ih < 0 || ih >= H) continue;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int iw = ow * 2 - 1 + s;
-        if (iw < 0 || iw >= W) continue;
-        float f[8];
-        Vec8<T>::load(in + (((int64_t)n * H + ih) * W + iw) * C + c8 * 8, f);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+        for (int s = 0; s < 3; ++s) {
+          const int iw = ow * 2 - 1 + s;
+          if (iw < 0 || iw >= W) continue;
+          const uint4 v = *reinterpret_cast<const uint4*>(img_in + ((int64_t)ih * W + iw) * C + c8 * 8);
+          m = first ? v : max8<T>(m, v);
+          first = false;
+        }
       }
+      *reinterpret_cast<uint4*>(img_out + (int64_t)i * 8) = m;
+    } else {
+      float m[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) m[k] = -INFINITY;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const int ih = oh * 2 - 1 + r;
+        if (ih < 0 || ih >= H) continue;
+#pragma unroll
+        for (int s = 0; s < 3; ++s) {
+          const int iw = ow * 2 - 1 + s;
+          if (iw < 0 || iw >= W) continue;
+          float f[8];
+          Vec8<T>::load(img_in + ((int64_t)ih * W + iw) * C + c8 * 8, f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) m[k] = fmaxf(m[k], f[k]);
+        }
+      }
+      Vec8<T>::store(img_out + (int64_t)i * 8, m);
     }
-    Vec8<T>::store(out + i * 8, m);
   }
 }
 
@@ -164,8 +199,9 @@ static int grid_for(int64_t total, int block) {
 template <typename T>
 static int pack_t(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int layout, cudaStream_t st) {
   if (layout == SEMDIFF_INPUT_S2D_ROW4) {
-    const int64_t total = (int64_t)2 * n_pairs * (H / 2 + 3) * (W / 2) * 4;
-    pack_s2d_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, H, W, (T*)out);
+    const int per_img = (H / 2 + 3) * (W / 2) * 4;
+    dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)(2 * n_pairs));
+    pack_s2d_kernel<T><<<grid, 256, 0, st>>>(gt, sr, n_pairs, H, W, (T*)out);
   } else {
     const int64_t total = (int64_t)2 * n_pairs * H * W;
     pack_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, H * W, (T*)out);
@@ -190,8 +226,9 @@ int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, voi
 template <typename T>
 static int maxpool_t(const void* in, void* out, int n, int H, int W, int C, cudaStream_t st) {
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
-  const int64_t total = (int64_t)n * OH * OW * (C / 8);
-  maxpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)in, (T*)out, n, H, W, C, OH, OW);
+  const int per_img = OH * OW * (C / 8);
+  dim3 grid((unsigned)std::min((per_img + 255) / 256, 128), (unsigned)n);
+  maxpool_kernel<T><<<grid, 256, 0, st>>>((const T*)in, (T*)out, H, W, C, OH, OW);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -7,12 +7,20 @@
 
 namespace semdiff {
 
+// A conv may read a SECOND activation tensor through a fused 1x1 conv (stride2, no padding) whose products are
+// accumulated into the same output: out = act(conv(in, W[:, :K1]) + conv1x1(in2, W[:, K1:]) + bias (+ res)).
+// This is how a ResNet projection shortcut (downsample conv) is folded into the block's last conv.
 struct ConvShape {
   int n_img, H, W, cin, cout, kh, kw, stride, pad, relu;
+  int cin2 = 0, stride2 = 1, H2 = 0, W2 = 0;
   int OH() const { return (H + 2 * pad - kh) / stride + 1; }
   int OW() const { return (W + 2 * pad - kw) / stride + 1; }
   int64_t M() const { return (int64_t)n_img * OH() * OW(); }
-  int K() const { return kh * kw * cin; }
+  int K1() const { return kh * kw * cin; }
+  int K() const { return kh * kw * cin + cin2; }
+};
+struct ConvPtrs {
+  const void* in; const void* in2; const void* w; const float* bias; const void* res; void* out;
 };
 
 inline size_t elem_bytes(int precision) { return precision == SEMDIFF_FP32 ? 4 : 2; }
@@ -23,20 +31,17 @@ int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, voi
 int launch_maxpool3x3s2(const void* in, void* out, int n_img, int H, int W, int c, int precision, cudaStream_t stream);
 int launch_avgpool(const void* in, void* out, int n_img, int H, int W, int c, int window, int precision,
                    cudaStream_t stream);
-int launch_conv_simt(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
-                     int precision, cudaStream_t stream);
+int launch_conv_simt(const ConvPtrs& ptr, const ConvShape& s, int precision, cudaStream_t stream);
 // tcgen05 path; use_tma lets the activation tile come through TMA (tiled for 1x1 stride 1, im2col mode otherwise);
 // false forces the cp.async software-im2col gather
-int launch_conv_tc(const void* in, const void* w, const float* bias, const void* res, void* out, const ConvShape& s,
-                   int precision, bool use_tma, cudaStream_t stream);
+int launch_conv_tc(const ConvPtrs& ptr, const ConvShape& s, int precision, bool use_tma, cudaStream_t stream);
 bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma);
 // prepared launch (TMA descriptors encoded once, reused while pointers and shapes stay the same)
 struct alignas(64) ConvTcLaunch {
-  unsigned char params[768];
+  unsigned char params[896];
   int block_n, a_mode, precision;
 };
-int conv_tc_prepare(ConvTcLaunch* L, const void* in, const void* w, const float* bias, const void* res, void* out,
-                    const ConvShape& s, int precision, bool use_tma);
+int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& ptr, const ConvShape& s, int precision, bool use_tma);
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream);
 
 int distance_parts(int hw, int c);

@@ -21,10 +21,11 @@ void set_error(const char* fmt, ...) {
 }
 
 struct BufShape { int h = 0, w = 0, c = 0; };
+struct Prepared;
 
 // everything that depends on (workspace address, images in the micro-batch, H, W)
 struct ShapePlan {
-  std::vector<BufShape> op_src, op_dst;        // per op
+  std::vector<BufShape> op_src, op_src2, op_dst;  // per op
   std::vector<int64_t> buf_offset;             // per buffer, bytes from the workspace base
   std::vector<ConvTcLaunch> tc;                // per op (valid where impl is a tcgen05 one)
   std::vector<int> impl;                       // per op: SEMDIFF_CONV_*
@@ -67,6 +68,7 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
   }
   buf_elems[0] = n_img * cur[0].h * cur[0].w * cur[0].c;
   S->op_src.assign(n_ops, BufShape());
+  S->op_src2.assign(n_ops, BufShape());
   S->op_dst.assign(n_ops, BufShape());
   for (int i = 0; i < n_ops; ++i) {
     const semdiff_op& op = P->ops[i];
@@ -79,6 +81,16 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
       case SEMDIFF_OP_CONV:
         if (in.c != op.cin) { set_error("op %d: cin %d != buffer channels %d", i, op.cin, in.c); return SEMDIFF_ERR_ARG; }
         out = BufShape{(in.h + 2 * op.pad - op.kh) / op.stride + 1, (in.w + 2 * op.pad - op.kw) / op.stride + 1, op.cout};
+        if (op.src2 >= 0) {
+          if (op.src2 >= P->n_bufs || cur[op.src2].c == 0) { set_error("op %d: bad second source buffer", i); return SEMDIFF_ERR_ARG; }
+          const BufShape b2 = cur[op.src2];
+          S->op_src2[i] = b2;
+          const int st2 = op.stride2 < 1 ? 1 : op.stride2;
+          if (b2.c != op.cin2 || (b2.h - 1) / st2 + 1 != out.h || (b2.w - 1) / st2 + 1 != out.w) {
+            set_error("op %d: second source %dx%dx%d (stride %d) does not map onto output %dx%d", i, b2.h, b2.w, b2.c, st2, out.h, out.w);
+            return SEMDIFF_ERR_ARG;
+          }
+        }
         if (op.res >= 0) {
           if (op.res >= P->n_bufs) { set_error("op %d: bad residual buffer", i); return SEMDIFF_ERR_ARG; }
           const BufShape r = cur[op.res];
@@ -94,7 +106,8 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
       default: set_error("op %d: unknown kind %d", i, op.kind); return SEMDIFF_ERR_ARG;
     }
     if (out.h <= 0 || out.w <= 0) { set_error("op %d: empty output (input %dx%d too small)", i, in.h, in.w); return SEMDIFF_ERR_ARG; }
-    if (op.dst <= 0 || op.dst >= P->n_bufs || op.dst == op.src || op.dst == op.res) {
+    if (op.dst <= 0 || op.dst >= P->n_bufs || op.dst == op.src || op.dst == op.res ||
+        (op.kind == SEMDIFF_OP_CONV && op.dst == op.src2)) {
       set_error("op %d: bad dst buffer %d", i, op.dst);
       return SEMDIFF_ERR_ARG;
     }
@@ -118,16 +131,27 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
 
 static int choose_impl(const semdiff_plan* P, const ConvShape& cs) {
   if (P->precision == SEMDIFF_FP32 || P->conv_impl == SEMDIFF_CONV_SIMT) return SEMDIFF_CONV_SIMT;
-  if (P->conv_impl != SEMDIFF_CONV_TC_GATHER && conv_tc_supported(cs, P->precision, true)) return SEMDIFF_CONV_TC_TMA;
+  if ((P->conv_impl != SEMDIFF_CONV_TC_GATHER || cs.cin2 != 0) && conv_tc_supported(cs, P->precision, true))
+    return SEMDIFF_CONV_TC_TMA;
   if (conv_tc_supported(cs, P->precision, false)) return SEMDIFF_CONV_TC_GATHER;
   return SEMDIFF_CONV_SIMT;
 }
 
-static ConvShape conv_shape(const semdiff_op& op, const BufShape& in, int n_img) {
+static ConvShape conv_shape(const semdiff_op& op, const BufShape& in, const BufShape& in2, int n_img) {
   ConvShape cs;
   cs.n_img = n_img; cs.H = in.h; cs.W = in.w; cs.cin = op.cin; cs.cout = op.cout; cs.kh = op.kh; cs.kw = op.kw;
   cs.stride = op.stride; cs.pad = op.pad; cs.relu = op.relu;
+  if (op.src2 >= 0) { cs.cin2 = op.cin2; cs.stride2 = op.stride2 < 1 ? 1 : op.stride2; cs.H2 = in2.h; cs.W2 = in2.w; }
   return cs;
+}
+static ConvPtrs conv_ptrs(const semdiff_op& op, const ShapePlan& S, char* ws) {
+  ConvPtrs q;
+  q.in = ws + S.buf_offset[op.src];
+  q.in2 = op.src2 >= 0 ? ws + S.buf_offset[op.src2] : nullptr;
+  q.w = op.weight; q.bias = op.bias;
+  q.res = op.res >= 0 ? ws + S.buf_offset[op.res] : nullptr;
+  q.out = ws + S.buf_offset[op.dst];
+  return q;
 }
 
 static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
@@ -137,13 +161,11 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
   for (int i = 0; i < n_ops; ++i) {
     const semdiff_op& op = P->ops[i];
     if (op.kind != SEMDIFF_OP_CONV) continue;
-    const ConvShape cs = conv_shape(op, S->op_src[i], 2 * pairs);
+    const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], 2 * pairs);
     const int impl = choose_impl(P, cs);
     S->impl[i] = impl;
     if (impl == SEMDIFF_CONV_TC_TMA || impl == SEMDIFF_CONV_TC_GATHER) {
-      int rc = conv_tc_prepare(&S->tc[i], ws + S->buf_offset[op.src], op.weight, op.bias,
-                               op.res >= 0 ? ws + S->buf_offset[op.res] : nullptr, ws + S->buf_offset[op.dst], cs,
-                               P->precision, impl == SEMDIFF_CONV_TC_TMA);
+      int rc = conv_tc_prepare(&S->tc[i], conv_ptrs(op, *S, ws), cs, P->precision, impl == SEMDIFF_CONV_TC_TMA);
       if (rc != 0) return rc;
     }
   }
@@ -315,8 +337,7 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
         char* dst = ws + S.buf_offset[op.dst];
         if (op.kind == SEMDIFF_OP_CONV) {
           if (S.impl[i] == SEMDIFF_CONV_SIMT) {
-            rc = launch_conv_simt(src, op.weight, op.bias, op.res >= 0 ? ws + S.buf_offset[op.res] : nullptr, dst,
-                                  conv_shape(op, in, 2 * cur), P->precision, st);
+            rc = launch_conv_simt(conv_ptrs(op, S, ws), conv_shape(op, in, S.op_src2[i], 2 * cur), P->precision, st);
           } else {
             rc = conv_tc_launch(&S.tc[i], st);
           }
@@ -347,21 +368,30 @@ int semdiff_pack_input(const float* gt, const float* sr, int32_t n_pairs, int32_
 
 int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out, int32_t n_img,
                    int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
-                   int32_t relu, int32_t precision, int32_t impl, semdiff_stream_t st_) {
+                   int32_t relu, const void* in2, int32_t H2, int32_t W2, int32_t cin2, int32_t stride2,
+                   int32_t precision, int32_t impl, semdiff_stream_t st_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(st_);
   ConvShape cs;
   cs.n_img = n_img; cs.H = H; cs.W = W; cs.cin = cin; cs.cout = cout; cs.kh = kh; cs.kw = kw; cs.stride = stride;
   cs.pad = pad; cs.relu = relu;
-  if (n_img <= 0 || cs.OH() <= 0 || cs.OW() <= 0 || stride < 1) { set_error("conv2d: bad shape"); return SEMDIFF_ERR_ARG; }
+  if (n_img <= 0 || stride < 1 || cs.OH() <= 0 || cs.OW() <= 0) { set_error("conv2d: bad shape"); return SEMDIFF_ERR_ARG; }
+  if (in2 != nullptr) {
+    cs.cin2 = cin2; cs.stride2 = stride2; cs.H2 = H2; cs.W2 = W2;
+    if (stride2 < 1 || cin2 <= 0 || (H2 - 1) / stride2 + 1 != cs.OH() || (W2 - 1) / stride2 + 1 != cs.OW()) {
+      set_error("conv2d: second source does not map onto the output grid");
+      return SEMDIFF_ERR_ARG;
+    }
+  }
   if (impl == SEMDIFF_CONV_AUTO) {
     semdiff_plan tmp;
     tmp.precision = precision;
     impl = choose_impl(&tmp, cs);
   }
+  ConvPtrs q{in, in2, weight, bias, residual, out};
   switch (impl) {
-    case SEMDIFF_CONV_SIMT: return launch_conv_simt(in, weight, bias, residual, out, cs, precision, st);
-    case SEMDIFF_CONV_TC_GATHER: return launch_conv_tc(in, weight, bias, residual, out, cs, precision, false, st);
-    case SEMDIFF_CONV_TC_TMA: return launch_conv_tc(in, weight, bias, residual, out, cs, precision, true, st);
+    case SEMDIFF_CONV_SIMT: return launch_conv_simt(q, cs, precision, st);
+    case SEMDIFF_CONV_TC_GATHER: return launch_conv_tc(q, cs, precision, false, st);
+    case SEMDIFF_CONV_TC_TMA: return launch_conv_tc(q, cs, precision, true, st);
   }
   set_error("conv2d: bad impl %d", impl);
   return SEMDIFF_ERR_ARG;

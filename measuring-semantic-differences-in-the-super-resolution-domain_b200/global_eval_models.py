@@ -49,7 +49,8 @@ class _Plan:
                 self._keep += [w, b]
                 w_ptr, b_ptr = w.data_ptr(), b.data_ptr()
             arr[i] = _lib.SemdiffOp(op["kind"], op["src"], op["dst"], op["res"], op["cin"], op["cout"], op["kh"],
-                                    op["kw"], op["stride"], op["pad"], op["relu"], op["tap"], w_ptr, b_ptr)
+                                    op["kw"], op["stride"], op["pad"], op["relu"], op["tap"], op["src2"], op["cin2"],
+                                    op["stride2"], w_ptr, b_ptr)
         handle = C.c_void_p()
         _lib.check(self.lib.semdiff_plan_create(arr, len(ops), self.program.n_bufs, self.precision,
                                                 self.program.input_layout, C.byref(handle)), "semdiff_plan_create")

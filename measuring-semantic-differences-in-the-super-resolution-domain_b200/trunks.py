@@ -164,12 +164,26 @@ class Program:
         self.n_bufs = 0
         self.input_layout = _lib.INPUT_NHWC8
 
-    def conv(self, conv, bn, src, dst, res=-1, relu=True, cin_pad=None):
+    def conv(self, conv, bn, src, dst, res=-1, relu=True, cin_pad=None, second=None):
+        """One fused conv+BN(+ReLU) op.  `second=(conv1x1, bn, src2)` folds a projection shortcut into the same
+        launch: its (folded) weights are appended along K and the kernel reads `src2` for those K columns, so
+        out = act(conv(src) + conv1x1(src2) + b + b2) never materialises the shortcut tensor."""
         w, b = fold_conv_bn(conv, bn, cin_pad)
-        self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=res, cin=w.shape[3], cout=w.shape[0],
-                             kh=w.shape[1], kw=w.shape[2], stride=conv.stride[0], pad=conv.padding[0],
-                             relu=int(relu), tap=-1, w=w, b=b,
-                             alg_k=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1]))
+        op = dict(kind=_lib.OP_CONV, src=src, dst=dst, res=res, cin=w.shape[3], cout=w.shape[0],
+                  kh=w.shape[1], kw=w.shape[2], stride=conv.stride[0], pad=conv.padding[0],
+                  relu=int(relu), tap=-1, src2=-1, cin2=0, stride2=1,
+                  alg_k=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1], n_convs=1)
+        w = w.reshape(w.shape[0], -1)
+        if second is not None:
+            conv2, bn2, src2 = second
+            assert conv2.kernel_size == (1, 1) and conv2.padding == (0, 0) and res == -1
+            w2, b2 = fold_conv_bn(conv2, bn2)
+            w = torch.cat([w, w2.reshape(w2.shape[0], -1)], dim=1)
+            b = b + b2
+            op.update(src2=src2, cin2=conv2.in_channels, stride2=conv2.stride[0], alg_k=op["alg_k"] + conv2.in_channels,
+                      n_convs=2)
+        op.update(w=w.contiguous(), b=b)
+        self.ops.append(op)
 
     def stem7_s2d(self, conv, bn, src, dst):
         """7x7 stride-2 pad-3 stem as a 4x1 stride-1 conv over the SEMDIFF_INPUT_S2D_ROW4 buffer (csrc/elementwise.cu):
@@ -185,23 +199,24 @@ class Program:
                 w2[:, r, 0, base:base + 3] = w[:, ky, kx, :]
         self.input_layout = _lib.INPUT_S2D_ROW4
         self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=-1, cin=64, cout=w.shape[0], kh=4, kw=1, stride=1,
-                             pad=0, relu=1, tap=-1, w=w2, b=b, alg_k=147))
+                             pad=0, relu=1, tap=-1, src2=-1, cin2=0, stride2=1, w=w2.reshape(w2.shape[0], -1).contiguous(),
+                             b=b, alg_k=147, n_convs=1))
 
     def pool(self, kind, src, dst, window):
         self.ops.append(dict(kind=kind, src=src, dst=dst, res=-1, cin=0, cout=0, kh=window, kw=window, stride=window,
-                             pad=0, relu=0, tap=-1, w=None, b=None))
+                             pad=0, relu=0, tap=-1, src2=-1, cin2=0, stride2=1, w=None, b=None))
 
     def tap(self, src, j):
         self.ops.append(dict(kind=_lib.OP_TAP, src=src, dst=-1, res=-1, cin=0, cout=0, kh=0, kw=0, stride=0, pad=0,
-                             relu=0, tap=j, w=None, b=None))
+                             relu=0, tap=j, src2=-1, cin2=0, stride2=1, w=None, b=None))
 
 
 def lower_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Program:
     """timm resnet50; taps = layer{s}.2.act3 for s in range(4-depth, 5)  (global_eval_models.py:701).
     s2d_stem=False keeps the stem as a channel-padded 7x7 conv (needed for odd image sizes)."""
     P = Program()
-    IN, A, B, T1, T2, DS = range(6)
-    P.n_bufs = 6
+    IN, A, B, T1, T2 = range(5)
+    P.n_bufs = 5
     c1 = clip.conv1
     if s2d_stem and c1.kernel_size == (7, 7) and c1.stride == (2, 2) and c1.padding == (3, 3) and c1.in_channels == 3:
         P.stem7_s2d(c1, clip.bn1, IN, T1)
@@ -215,13 +230,12 @@ def lower_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Progra
             y = B if x == A else A
             P.conv(blk.conv1, blk.bn1, x, T1)
             P.conv(blk.conv2, blk.bn2, T1, T2)
-            res = x
             ds = getattr(blk, "downsample", None)
-            if ds is not None:
+            if ds is not None:   # projection shortcut folded into conv3's launch (K = planes + inplanes)
                 dconv, dbn = list(ds.children())[:2]
-                P.conv(dconv, dbn, x, DS, relu=False)
-                res = DS
-            P.conv(blk.conv3, blk.bn3, T2, y, res=res)
+                P.conv(blk.conv3, blk.bn3, T2, y, second=(dconv, dbn, x))
+            else:
+                P.conv(blk.conv3, blk.bn3, T2, y, res=x)
             x = y
             if bi == 2 and li >= 4 - depth:
                 P.tap(x, li - (4 - depth))
@@ -231,8 +245,8 @@ def lower_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Progra
 def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Program:
     """timm resnet50_clip.openai; taps = stages.{s}.2.act for s in range(3-depth, 4)  (global_eval_models.py:327)."""
     P = Program()
-    IN, A, B, T1, T2, T3, D0, DS = range(8)
-    P.n_bufs = 8
+    IN, A, B, T1, T2, T3, D0 = range(7)
+    P.n_bufs = 7
     st = clip.stem
     P.conv(st.conv1.conv, st.conv1.bn, IN, T1, cin_pad=8)
     P.conv(st.conv2.conv, st.conv2.bn, T1, T2)
@@ -249,16 +263,15 @@ def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> P
             if stride > 1:
                 P.pool(_lib.OP_AVGPOOL, T2, T3, stride)
                 mid = T3
-            res = x
             sc = getattr(blk, "shortcut", None)
-            if sc is not None:
+            if sc is not None:   # avg-pool + 1x1 projection shortcut: the 1x1 is folded into conv3's launch
                 sx = x
                 if stride > 1:
                     P.pool(_lib.OP_AVGPOOL, x, D0, stride)
                     sx = D0
-                P.conv(sc.conv.conv, sc.conv.bn, sx, DS, relu=False)
-                res = DS
-            P.conv(blk.conv3_1x1.conv, blk.conv3_1x1.bn, mid, y, res=res)
+                P.conv(blk.conv3_1x1.conv, blk.conv3_1x1.bn, mid, y, second=(sc.conv.conv, sc.conv.bn, sx))
+            else:
+                P.conv(blk.conv3_1x1.conv, blk.conv3_1x1.bn, mid, y, res=x)
             x = y
             if bi == 2 and si >= 3 - depth:
                 P.tap(x, si - (3 - depth))

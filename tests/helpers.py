@@ -27,14 +27,23 @@ def nchw(x: torch.Tensor) -> torch.Tensor:
     return x.float().permute(0, 3, 1, 2).contiguous()
 
 
-def conv2d(x_nhwc, w_ohwi, bias, residual, stride, pad, relu, precision: str, impl: int):
+def conv2d(x_nhwc, w_ohwi, bias, residual, stride, pad, relu, precision: str, impl: int, x2_nhwc=None, w2=None,
+           stride2=1):
+    """w_ohwi [Cout,KH,KW,Cin]; optional fused second source x2 [n,H2,W2,Cin2] with 1x1 weights w2 [Cout,Cin2]."""
     n, H, W, cin = x_nhwc.shape
     cout, kh, kw, _ = w_ohwi.shape
     oh, ow = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
     out = torch.empty(n, oh, ow, cout, dtype=x_nhwc.dtype, device=x_nhwc.device)
-    rc = lib().semdiff_conv2d(x_nhwc.data_ptr(), w_ohwi.data_ptr(), bias.data_ptr(),
+    wmat = w_ohwi.reshape(cout, -1)
+    H2 = W2 = cin2 = 0
+    if x2_nhwc is not None:
+        _, H2, W2, cin2 = x2_nhwc.shape
+        wmat = torch.cat([wmat, w2], dim=1)
+    wmat = wmat.contiguous()
+    rc = lib().semdiff_conv2d(x_nhwc.data_ptr(), wmat.data_ptr(), bias.data_ptr(),
                               residual.data_ptr() if residual is not None else None, out.data_ptr(), n, H, W, cin, cout,
-                              kh, kw, stride, pad, int(relu), _lib.PRECISIONS[precision], impl, sp())
+                              kh, kw, stride, pad, int(relu), x2_nhwc.data_ptr() if x2_nhwc is not None else None,
+                              H2, W2, cin2, stride2, _lib.PRECISIONS[precision], impl, sp())
     _lib.check(rc, "semdiff_conv2d")
     return out
 

@@ -68,12 +68,13 @@ def test_lowering(name, convs, gflop):
     assert abs(trunks.conv_flops(generic, 224, 224) / 1e9 - gflop) < 1e-9
     for depth in range(4):
         prog = trunks.LOWER[name](tree, depth)
-        assert sum(op["kind"] == _lib.OP_CONV for op in prog.ops) == convs
+        assert sum(op.get("n_convs", 0) for op in prog.ops) == convs            # every reference conv is covered
+        assert sum(op["kind"] == _lib.OP_CONV for op in prog.ops) == convs - 4  # 4 projection shortcuts are fused
         taps = [op["tap"] for op in prog.ops if op["kind"] == _lib.OP_TAP]
         assert taps == list(range(depth + 1))
         for op in prog.ops:   # a conv never reads or adds the buffer it writes
             if op["kind"] != _lib.OP_TAP:
-                assert op["dst"] not in (op["src"], op["res"]) and 0 < op["dst"] < prog.n_bufs
+                assert op["dst"] not in (op["src"], op["res"], op["src2"]) and 0 < op["dst"] < prog.n_bufs
     assert abs(trunks.conv_flops(prog, 224, 224) / 1e9 - gflop) < 1e-9   # SURVEY.md 8d algorithmic FLOPs
 
 
@@ -116,6 +117,6 @@ def test_s2d_stem_weights_reproduce_the_7x7_conv():
                         y, xx = 2 * (i - 2) + dy, 2 * (q - 2 + j) + dx
                         if 0 <= y < H and 0 <= xx < W:
                             X2[:, i, q, j * 16 + (dy * 2 + dx) * 3: j * 16 + (dy * 2 + dx) * 3 + 3] = x[:, :, y, xx]
-    got = torch.nn.functional.conv2d(X2.permute(0, 3, 1, 2), op["w"].permute(0, 3, 1, 2), op["b"])
+    got = torch.nn.functional.conv2d(X2.permute(0, 3, 1, 2), op["w"].reshape(64, 4, 1, 64).permute(0, 3, 1, 2), op["b"])
     ref = tree.bn1.double().eval()(tree.conv1.double()(x))
     assert got.shape == ref.shape and torch.allclose(got, ref, rtol=1e-10, atol=1e-10)

@@ -114,6 +114,26 @@ def test_conv_simt_bf16(case):
     assert torch.allclose(out, ref, rtol=8e-3, atol=8e-3), (out - ref).abs().max().item()
 
 
+@pytest.mark.parametrize("precision,impl", [("fp32", _lib.CONV_SIMT), ("bf16", _lib.CONV_SIMT), ("bf16", _lib.CONV_TC_TMA)])
+@pytest.mark.parametrize("geom", [(2, 56, 56, 64, 64, 256, 1), (3, 14, 14, 256, 512, 1024, 2), (1, 7, 7, 512, 1024, 2048, 2)])
+def test_conv_with_fused_projection_shortcut(geom, precision, impl):
+    """conv3(t2) + downsample(x) in ONE launch (second activation source appended along K)."""
+    n, oh, ow, c1, c2, cout, s2 = geom
+    g = torch.Generator(device=DEV).manual_seed(7)
+    dt = DT[precision]
+    x1 = torch.randn(n, oh, ow, c1, device=DEV, generator=g).to(dt)
+    H2, W2 = oh * s2, ow * s2
+    x2 = torch.randn(n, H2, W2, c2, device=DEV, generator=g).to(dt)
+    w1 = (torch.randn(cout, 1, 1, c1, device=DEV, generator=g) * (1.0 / c1) ** 0.5).to(dt)
+    w2 = (torch.randn(cout, c2, device=DEV, generator=g) * (1.0 / c2) ** 0.5).to(dt)
+    b = torch.randn(cout, device=DEV, generator=g) * 0.1
+    out = conv2d(x1, w1, b, None, 1, 0, True, precision, impl, x2_nhwc=x2, w2=w2, stride2=s2).double()
+    ref = conv_reference(x1, w1, b, None, 1, 0, False) + conv_reference(x2, w2.reshape(cout, 1, 1, c2), torch.zeros_like(b), None, s2, 0, False)
+    ref = torch.relu(ref)
+    tol = 2e-5 if precision == "fp32" else 8e-3
+    assert torch.allclose(out, ref, rtol=tol, atol=tol), (out - ref).abs().max().item()
+
+
 def _distance_ref(act, n_pairs, w):
     a, b = act[:n_pairs].double(), act[n_pairs:].double()
     return (((a - b) ** 2) * w.double()).sum(dim=(1, 2))
