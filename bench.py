@@ -222,14 +222,24 @@ def main():
     # ---- e2e: host buffers in, host scores out, through the public API -------------------------
     gt_h = torch.empty(n, 3, H, W, pin_memory=True).copy_(gt)
     sr_h = torch.empty(n, 3, H, W, pin_memory=True).copy_(sr)
-    out_h = torch.empty(n, pin_memory=True)
-    e2e_steps = max(3, args.steps // 2)
-    for _ in range(2):
-        model.score_host(gt_h, sr_h, out_h)
+    outs_h = [torch.empty(n, pin_memory=True) for _ in range(2)]
+    e2e_steps = max(4, args.steps // 2)
+
+    def e2e_loop(k):
+        """k steps, two in flight: step i+1's images cross PCIe while step i is scored; every step's scores are read
+        back to the host and waited for."""
+        pending = None
+        for i in range(k):
+            _, ev = model.score_host(gt_h, sr_h, outs_h[i % 2], wait=False)
+            if pending is not None:
+                pending.synchronize()
+            pending = ev
+        pending.synchronize()
+
+    e2e_loop(3)
     barrier()
     e0.record()
-    for _ in range(e2e_steps):
-        model.score_host(gt_h, sr_h, out_h)     # synchronises: the scores are on the host when it returns
+    e2e_loop(e2e_steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
@@ -238,10 +248,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_e2e = t.item()
     e2e = {"value": total_pairs * e2e_steps / (ms_e2e / 1e3), "unit": UNIT,
-           "h2d_bytes_per_step": 2 * gt_h.numel() * 4, "d2h_bytes_per_step": out_h.numel() * 4,
+           "h2d_bytes_per_step": 2 * gt_h.numel() * 4, "d2h_bytes_per_step": outs_h[0].numel() * 4,
            "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-           "how": "model.score_host(pinned gt, pinned sr) -> pinned scores: chunked H2D on a copy stream overlapped with scoring"}
-    assert torch.allclose(out_h, scores[rank * n:(rank + 1) * n].cpu() if world > 1 else scores.cpu(), rtol=0, atol=0), "e2e result differs"
+           "how": "model.score_host(pinned fp32 gt, pinned fp32 sr) -> pinned scores, two steps in flight: the H2D copy "
+                  "of step i+1 (copy stream, 2 staging slots) overlaps the scoring of step i; PCIe-bound above ~43k pairs/s "
+                  "(308 MB per 256 pairs at the measured 51.7 GB/s)"}
+    ref_scores = scores[rank * n:(rank + 1) * n].cpu() if world > 1 else scores.cpu()
+    assert torch.equal(outs_h[0], ref_scores) and torch.equal(outs_h[1], ref_scores), "e2e result differs"
 
     # ---- roofline of the dominant kernel family (tcgen05 implicit-GEMM convs), per-op CUDA events ----
     plan = model.plan()

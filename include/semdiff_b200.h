@@ -72,9 +72,11 @@ typedef struct semdiff_op {
 
 typedef struct semdiff_plan semdiff_plan;
 
-/* Build an execution plan for a trunk program.  Copies the op list (not the weights). */
+/* Build an execution plan for a trunk program.  Copies the op list (not the weights).
+ * head_ops: the first `head_ops` ops (stem convs + first pooling op, no residuals/taps) may be run in chunks of images
+ * sized so that their activations stay L2-resident between kernels (0 = never chunk; results are identical). */
 int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision,
-                        int32_t input_layout, semdiff_plan** out_plan);
+                        int32_t input_layout, int32_t head_ops, semdiff_plan** out_plan);
 int semdiff_plan_destroy(semdiff_plan* plan);
 /* Force the conv implementation of every conv op (SEMDIFF_CONV_*; AUTO = best supported). Testing aid. */
 int semdiff_plan_set_conv_impl(semdiff_plan* plan, int32_t impl);

@@ -28,7 +28,7 @@ class SemdiffOp(C.Structure):
 # name -> (restype, argtypes); every symbol include/semdiff_b200.h declares
 _P, _I, _L = C.c_void_p, C.c_int32, C.c_int64
 SIGNATURES = {
-    "semdiff_plan_create": (_I, [C.POINTER(SemdiffOp), _I, _I, _I, _I, C.POINTER(_P)]),
+    "semdiff_plan_create": (_I, [C.POINTER(SemdiffOp), _I, _I, _I, _I, _I, C.POINTER(_P)]),
     "semdiff_plan_destroy": (_I, [_P]),
     "semdiff_plan_set_conv_impl": (_I, [_P, _I]),
     "semdiff_workspace_bytes": (_L, [_P, _I, _I, _I]),

@@ -11,11 +11,11 @@ namespace semdiff {
 // plane reads are coalesced across the warp, the write is one 16 B (32 B for fp32) vector per thread.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ gt, const float* __restrict__ sr,
-                                                   int n_pairs, int hw, T* __restrict__ out) {
-  const int64_t total = (int64_t)2 * n_pairs * hw;
+                                                   int n_pairs, int img0, int n_imgs, int hw, T* __restrict__ out) {
+  const int64_t total = (int64_t)n_imgs * hw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int img = (int)(i / hw);
-    const int pix = (int)(i - (int64_t)img * hw);
+    const int img = img0 + (int)(i / hw);
+    const int pix = (int)(i % hw);
     const float* src = (img < n_pairs ? gt + (int64_t)img * 3 * hw : sr + (int64_t)(img - n_pairs) * 3 * hw) + pix;
     float f[8] = {__ldg(src), __ldg(src + hw), __ldg(src + 2 * hw), 0.f, 0.f, 0.f, 0.f, 0.f};
     if constexpr (sizeof(T) == 2) {
@@ -36,13 +36,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ gt,
 // 49 x 8 a channel-padded 7x7 window would need.  One thread per (img, i, q, j): 6 float2 reads, 32 bytes written.
 template <typename T>
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ gt, const float* __restrict__ sr,
-                                                       int n_pairs, int H, int W, T* __restrict__ out) {
+                                                       int n_pairs, int img0, int H, int W, T* __restrict__ out) {
   const int H2 = H / 2 + 3, W2 = W / 2;
   const int per_img = H2 * W2 * 4;
-  const int img = blockIdx.y;
+  const int img = img0 + blockIdx.y;
   const int plane = H * W;
   const float* src = img < n_pairs ? gt + (int64_t)img * 3 * plane : sr + (int64_t)(img - n_pairs) * 3 * plane;
-  T* out_img = out + (int64_t)img * per_img * 16;
+  T* out_img = out + (int64_t)blockIdx.y * per_img * 16;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += gridDim.x * blockDim.x) {
     const int j = t & 3;
     const int r = t >> 2;
@@ -197,27 +197,31 @@ static int grid_for(int64_t total, int block) {
 }
 
 template <typename T>
-static int pack_t(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int layout, cudaStream_t st) {
+static int pack_t(const float* gt, const float* sr, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
+                  int layout, cudaStream_t st) {
   if (layout == SEMDIFF_INPUT_S2D_ROW4) {
     const int per_img = (H / 2 + 3) * (W / 2) * 4;
-    dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)(2 * n_pairs));
-    pack_s2d_kernel<T><<<grid, 256, 0, st>>>(gt, sr, n_pairs, H, W, (T*)out);
+    dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)n_imgs);
+    pack_s2d_kernel<T><<<grid, 256, 0, st>>>(gt, sr, n_pairs, img0, H, W, (T*)out);
   } else {
-    const int64_t total = (int64_t)2 * n_pairs * H * W;
-    pack_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, H * W, (T*)out);
+    const int64_t total = (int64_t)n_imgs * H * W;
+    pack_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, img0, n_imgs, H * W, (T*)out);
   }
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_pack(const float* gt, const float* sr, int n_pairs, int H, int W, void* out, int precision, int layout,
-                cudaStream_t st) {
-  if (n_pairs <= 0 || H <= 0 || W <= 0) { set_error("pack: bad shape"); return SEMDIFF_ERR_ARG; }
+int launch_pack(const float* gt, const float* sr, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
+                int precision, int layout, cudaStream_t st) {
+  if (n_pairs <= 0 || H <= 0 || W <= 0 || img0 < 0 || n_imgs <= 0 || img0 + n_imgs > 2 * n_pairs) {
+    set_error("pack: bad shape");
+    return SEMDIFF_ERR_ARG;
+  }
   if (layout == SEMDIFF_INPUT_S2D_ROW4 && ((H | W) & 1)) { set_error("pack: the s2d stem layout needs even H and W"); return SEMDIFF_ERR_ARG; }
   if (layout != SEMDIFF_INPUT_NHWC8 && layout != SEMDIFF_INPUT_S2D_ROW4) { set_error("pack: bad layout %d", layout); return SEMDIFF_ERR_ARG; }
   switch (precision) {
-    case SEMDIFF_BF16: return pack_t<__nv_bfloat16>(gt, sr, n_pairs, H, W, out, layout, st);
-    case SEMDIFF_FP16: return pack_t<__half>(gt, sr, n_pairs, H, W, out, layout, st);
-    case SEMDIFF_FP32: return pack_t<float>(gt, sr, n_pairs, H, W, out, layout, st);
+    case SEMDIFF_BF16: return pack_t<__nv_bfloat16>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+    case SEMDIFF_FP16: return pack_t<__half>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+    case SEMDIFF_FP32: return pack_t<float>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
   }
   set_error("pack: bad precision %d", precision);
   return SEMDIFF_ERR_ARG;

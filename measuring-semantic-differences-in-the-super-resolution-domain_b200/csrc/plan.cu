@@ -1,6 +1,7 @@
 // Host side of libsemdiff_b200.so: the trunk "program" executor (plan) and the C-ABI (include/semdiff_b200.h).
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -28,7 +29,9 @@ struct ShapePlan {
   std::vector<BufShape> op_src, op_src2, op_dst;  // per op
   std::vector<int64_t> buf_offset;             // per buffer, bytes from the workspace base
   std::vector<ConvTcLaunch> tc;                // per op (valid where impl is a tcgen05 one)
+  std::vector<ConvTcLaunch> tc_tail;           // head ops only: launch for the ragged last chunk
   std::vector<int> impl;                       // per op: SEMDIFF_CONV_*
+  int chunk_imgs = 0;                          // images per head chunk (0 = head ops run on the whole micro-batch)
   int64_t partial_offset = 0;
   int64_t total_bytes = 0;
   bool prepared = false;
@@ -42,6 +45,11 @@ using namespace semdiff;
 struct semdiff_plan {
   std::vector<semdiff_op> ops;
   int n_bufs = 0, precision = 0, n_taps = 0, conv_impl = SEMDIFF_CONV_AUTO, input_layout = SEMDIFF_INPUT_NHWC8;
+  // The first `head_ops` ops (stem + first pool) stream the widest activations of the trunk.  They run in chunks of
+  // images small enough that pack output and stem output stay L2-resident between the three kernels (the buffers are
+  // reused by every chunk, so the lines are overwritten in cache instead of travelling to HBM and back).
+  int head_ops = 0;
+  int64_t head_l2_bytes = 0;  // measured on B200 (profiles/r1_head_chunking.txt): chunking loses 3-6 %, so it is off unless SEMDIFF_HEAD_L2_MB is set
   std::vector<int> tap_c, tap_off;  // channels and head_w offset per tap
   int chan_total = 0;
   std::map<std::tuple<int, int, int>, ShapePlan> shapes;  // key: (pairs in micro-batch, H, W)
@@ -66,7 +74,29 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
   } else {
     cur[0] = BufShape{H, W, 8};
   }
-  buf_elems[0] = n_img * cur[0].h * cur[0].w * cur[0].c;
+  S->chunk_imgs = 0;
+  if (P->head_ops > 0) {
+    // per-image bytes of the buffers that live only inside a head chunk: the packed input + every head output but the last
+    int64_t per_img = (int64_t)cur[0].h * cur[0].w * cur[0].c;
+    std::vector<BufShape> t(P->n_bufs);
+    t[0] = cur[0];
+    for (int i = 0; i + 1 < P->head_ops; ++i) {
+      const semdiff_op& op = P->ops[i];
+      const BufShape in = t[op.src];
+      BufShape o = in;
+      if (op.kind == SEMDIFF_OP_CONV) o = BufShape{(in.h + 2 * op.pad - op.kh) / op.stride + 1, (in.w + 2 * op.pad - op.kw) / op.stride + 1, op.cout};
+      else if (op.kind == SEMDIFF_OP_MAXPOOL3S2) o = BufShape{(in.h - 1) / 2 + 1, (in.w - 1) / 2 + 1, in.c};
+      else if (op.kind == SEMDIFF_OP_AVGPOOL) o = BufShape{in.h / op.stride, in.w / op.stride, in.c};
+      t[op.dst] = o;
+      per_img += (int64_t)o.h * o.w * o.c;
+    }
+    per_img *= (int64_t)elem_bytes(P->precision);
+    int64_t c = P->head_l2_bytes / (per_img > 0 ? per_img : 1);
+    if (c < 1) c = 1;
+    if (c < n_img) S->chunk_imgs = (int)c;   // otherwise the whole micro-batch already fits: no chunking
+  }
+  const int64_t head_img = S->chunk_imgs > 0 ? S->chunk_imgs : n_img;
+  buf_elems[0] = head_img * cur[0].h * cur[0].w * cur[0].c;
   S->op_src.assign(n_ops, BufShape());
   S->op_src2.assign(n_ops, BufShape());
   S->op_dst.assign(n_ops, BufShape());
@@ -113,7 +143,7 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
     }
     S->op_dst[i] = out;
     cur[op.dst] = out;
-    const int64_t e = n_img * out.h * out.w * out.c;
+    const int64_t e = (i + 1 < P->head_ops ? head_img : n_img) * out.h * out.w * out.c;
     if (e > buf_elems[op.dst]) buf_elems[op.dst] = e;
   }
   S->buf_offset.assign(P->n_bufs, 0);
@@ -157,16 +187,25 @@ static ConvPtrs conv_ptrs(const semdiff_op& op, const ShapePlan& S, char* ws) {
 static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
   const int n_ops = (int)P->ops.size();
   S->tc.resize(n_ops);
+  S->tc_tail.resize(n_ops);
   S->impl.assign(n_ops, 0);
+  const int chunk = S->chunk_imgs, tail = chunk > 0 ? (2 * pairs) % chunk : 0;
   for (int i = 0; i < n_ops; ++i) {
     const semdiff_op& op = P->ops[i];
     if (op.kind != SEMDIFF_OP_CONV) continue;
-    const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], 2 * pairs);
+    const bool in_head = chunk > 0 && i < P->head_ops;
+    if (in_head && i + 1 == P->head_ops) { set_error("the last head op must be a pooling op"); return SEMDIFF_ERR_UNSUPPORTED; }
+    const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], in_head ? chunk : 2 * pairs);
     const int impl = choose_impl(P, cs);
     S->impl[i] = impl;
     if (impl == SEMDIFF_CONV_TC_TMA || impl == SEMDIFF_CONV_TC_GATHER) {
       int rc = conv_tc_prepare(&S->tc[i], conv_ptrs(op, *S, ws), cs, P->precision, impl == SEMDIFF_CONV_TC_TMA);
       if (rc != 0) return rc;
+      if (in_head && tail > 0) {
+        const ConvShape ct = conv_shape(op, S->op_src[i], S->op_src2[i], tail);
+        rc = conv_tc_prepare(&S->tc_tail[i], conv_ptrs(op, *S, ws), ct, P->precision, impl == SEMDIFF_CONV_TC_TMA);
+        if (rc != 0) return rc;
+      }
     }
   }
   S->prepared = true;
@@ -193,12 +232,17 @@ const char* semdiff_last_error(void) { return g_err; }
 const char* semdiff_version(void) { return "semdiff_b200 0.1 sm_100a"; }
 
 int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision, int32_t input_layout,
-                        semdiff_plan** out) {
+                        int32_t head_ops, semdiff_plan** out) {
   if (ops == nullptr || out == nullptr || n_ops <= 0 || n_bufs < 2) { set_error("plan_create: bad arguments"); return SEMDIFF_ERR_ARG; }
   if (precision < SEMDIFF_BF16 || precision > SEMDIFF_FP32) { set_error("plan_create: bad precision %d", precision); return SEMDIFF_ERR_ARG; }
   if (input_layout != SEMDIFF_INPUT_NHWC8 && input_layout != SEMDIFF_INPUT_S2D_ROW4) { set_error("plan_create: bad input layout %d", input_layout); return SEMDIFF_ERR_ARG; }
   semdiff_plan* P = new semdiff_plan();
   P->input_layout = input_layout;
+  P->head_ops = head_ops < 0 || head_ops > n_ops ? 0 : head_ops;
+  if (const char* e = getenv("SEMDIFF_HEAD_L2_MB")) P->head_l2_bytes = (int64_t)atoll(e) << 20;  // 0 disables chunking
+  if (P->head_l2_bytes <= 0) P->head_ops = 0;
+  for (int i = 0; i < P->head_ops; ++i)
+    if (ops[i].kind == SEMDIFF_OP_TAP || ops[i].res >= 0 || ops[i].src2 >= 0) P->head_ops = 0;  // keep the head simple
   P->ops.assign(ops, ops + n_ops);
   P->n_bufs = n_bufs;
   P->precision = precision;
@@ -311,14 +355,11 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
     }
     float* partials = reinterpret_cast<float*>(ws + S.partial_offset);
     int tap_parts[16], tap_hw[16];
-    {
-      ProfScope ps(P, n_ops + 0, st);
-      int rc = launch_pack(gt + p0 * img_elems, sr + p0 * img_elems, cur, H, W, ws + S.buf_offset[0], P->precision,
-                           P->input_layout, st);
-      if (rc != 0) return rc;
-      P->last_launches++;
-    }
-    for (int i = 0; i < n_ops; ++i) {
+    const int n_img = 2 * cur;
+    const float* gt_mb = gt + p0 * img_elems;
+    const float* sr_mb = sr + p0 * img_elems;
+    // one op on `imgs` images; dst_img0 offsets the destination (head chunks write into the full-batch buffer)
+    auto run_op = [&](int i, int imgs, int dst_img0, bool tail_launch) -> int {
       const semdiff_op& op = P->ops[i];
       const BufShape in = S.op_src[i];
       char* src = ws + S.buf_offset[op.src];
@@ -332,22 +373,52 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
         rc = launch_distance(src, cur, hw, in.c, head_w + P->tap_off[j], normalize,
                              partials + (int64_t)j * cur * SEMDIFF_MAX_PARTS, cm, P->chan_total, P->precision, st);
         P->last_launches += cm ? 2 : 1;
-      } else {
-        ProfScope ps(P, i, st);
-        char* dst = ws + S.buf_offset[op.dst];
-        if (op.kind == SEMDIFF_OP_CONV) {
-          if (S.impl[i] == SEMDIFF_CONV_SIMT) {
-            rc = launch_conv_simt(conv_ptrs(op, S, ws), conv_shape(op, in, S.op_src2[i], 2 * cur), P->precision, st);
-          } else {
-            rc = conv_tc_launch(&S.tc[i], st);
-          }
-        } else if (op.kind == SEMDIFF_OP_MAXPOOL3S2) {
-          rc = launch_maxpool3x3s2(src, dst, 2 * cur, in.h, in.w, in.c, P->precision, st);
-        } else {
-          rc = launch_avgpool(src, dst, 2 * cur, in.h, in.w, in.c, op.stride, P->precision, st);
-        }
-        P->last_launches++;
+        return rc;
       }
+      ProfScope ps(P, i, st);
+      const BufShape o = S.op_dst[i];
+      char* dst = ws + S.buf_offset[op.dst] + (int64_t)dst_img0 * o.h * o.w * o.c * (int64_t)elem_bytes(P->precision);
+      if (op.kind == SEMDIFF_OP_CONV) {
+        if (S.impl[i] == SEMDIFF_CONV_SIMT) {
+          ConvPtrs q = conv_ptrs(op, S, ws);
+          q.out = dst;
+          rc = launch_conv_simt(q, conv_shape(op, in, S.op_src2[i], imgs), P->precision, st);
+        } else {
+          rc = conv_tc_launch(tail_launch ? &S.tc_tail[i] : &S.tc[i], st);
+        }
+      } else if (op.kind == SEMDIFF_OP_MAXPOOL3S2) {
+        rc = launch_maxpool3x3s2(src, dst, imgs, in.h, in.w, in.c, P->precision, st);
+      } else {
+        rc = launch_avgpool(src, dst, imgs, in.h, in.w, in.c, op.stride, P->precision, st);
+      }
+      P->last_launches++;
+      return rc;
+    };
+    int first_op = 0;
+    if (S.chunk_imgs > 0) {
+      // head: pack -> stem -> pool per L2-sized chunk of images
+      for (int c0 = 0; c0 < n_img; c0 += S.chunk_imgs) {
+        const int cn = n_img - c0 < S.chunk_imgs ? n_img - c0 : S.chunk_imgs;
+        {
+          ProfScope ps(P, n_ops + 0, st);
+          int rc = launch_pack(gt_mb, sr_mb, cur, c0, cn, H, W, ws + S.buf_offset[0], P->precision, P->input_layout, st);
+          if (rc != 0) return rc;
+          P->last_launches++;
+        }
+        for (int i = 0; i < P->head_ops; ++i) {
+          int rc = run_op(i, cn, i + 1 == P->head_ops ? c0 : 0, cn != S.chunk_imgs);
+          if (rc != 0) return rc;
+        }
+      }
+      first_op = P->head_ops;
+    } else {
+      ProfScope ps(P, n_ops + 0, st);
+      int rc = launch_pack(gt_mb, sr_mb, cur, 0, n_img, H, W, ws + S.buf_offset[0], P->precision, P->input_layout, st);
+      if (rc != 0) return rc;
+      P->last_launches++;
+    }
+    for (int i = first_op; i < n_ops; ++i) {
+      int rc = run_op(i, n_img, 0, false);
       if (rc != 0) return rc;
     }
     {
@@ -363,7 +434,7 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
 
 int semdiff_pack_input(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
                        int32_t precision, int32_t layout, semdiff_stream_t st) {
-  return launch_pack(gt, sr, n_pairs, H, W, out, precision, layout, reinterpret_cast<cudaStream_t>(st));
+  return launch_pack(gt, sr, n_pairs, 0, 2 * n_pairs, H, W, out, precision, layout, reinterpret_cast<cudaStream_t>(st));
 }
 
 int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out, int32_t n_img,

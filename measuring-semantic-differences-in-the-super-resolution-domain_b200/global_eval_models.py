@@ -53,7 +53,8 @@ class _Plan:
                                     op["stride2"], w_ptr, b_ptr)
         handle = C.c_void_p()
         _lib.check(self.lib.semdiff_plan_create(arr, len(ops), self.program.n_bufs, self.precision,
-                                                self.program.input_layout, C.byref(handle)), "semdiff_plan_create")
+                                                self.program.input_layout, self.program.head_ops, C.byref(handle)),
+                   "semdiff_plan_create")
         self.handle = handle
         self.n_ops = len(ops)
         self.device = device
@@ -231,47 +232,57 @@ class _B200Scorer(nn.Module):
 
     @torch.no_grad()
     def score_host(self, gt_host: torch.Tensor, sr_host: torch.Tensor, out_host: torch.Tensor | None = None,
-                   chunk_pairs: int = 64) -> torch.Tensor:
+                   chunk_pairs: int | None = None, wait: bool = True):
         """End-to-end scoring of HOST tensors (pinned fp32 [N,3,H,W]) -> host scores [N].
 
-        The images cross PCIe in chunks on a copy stream into two staging buffers while the previous chunk is
-        scored on the current stream, so the transfer overlaps the kernels; the call returns once the scores are
-        on the host.  Chunking does not change any pair's arithmetic."""
+        The images cross PCIe on a copy stream into a ring of two device staging slots while the previous slot is
+        being scored on the current stream, so the transfer overlaps the kernels - within one call when it spans
+        several chunks, and across calls when the caller keeps two calls in flight (`wait=False` returns
+        `(out_host, event)`; the scores are valid after `event.synchronize()`).  Chunking does not change any pair's
+        arithmetic."""
         n, _, H, W = gt_host.shape
         dev = self._device
         if out_host is None:
             out_host = torch.empty(n, dtype=torch.float32, pin_memory=True)
+        main = torch.cuda.current_stream(dev)
+        done = torch.cuda.Event()
         if n == 0:
-            return out_host
+            done.record(main)
+            return out_host if wait else (out_host, done)
         head_w = torch.cat([m.weight.reshape(-1) for m in self.w_layers]).float()
         head_b = torch.cat([m.bias.reshape(-1) for m in self.w_layers]).float()
-        chunk = min(chunk_pairs, n)
+        chunk = min(chunk_pairs or self.default_microbatch(H, W), n)
         if getattr(self, "_stage_shape", None) != (chunk, H, W):
+            torch.cuda.synchronize(dev)
             self._stage = [(torch.empty(chunk, 3, H, W, device=dev), torch.empty(chunk, 3, H, W, device=dev)) for _ in range(2)]
+            self._stage_consumed = [None, None]       # event: the scoring that last read this slot has finished
+            self._stage_next = 0
             self._stage_shape = (chunk, H, W)
             self._copy_stream = torch.cuda.Stream(device=dev)
         out_dev = torch.empty(n, dtype=torch.float32, device=dev)
-        main = torch.cuda.current_stream(dev)
-        copied = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
-        n_chunks = (n + chunk - 1) // chunk
-        for i in range(n_chunks):
-            lo, hi = i * chunk, min(n, (i + 1) * chunk)
-            g_buf, s_buf = self._stage[i % 2]
+        for lo in range(0, n, chunk):
+            hi = min(n, lo + chunk)
+            slot = self._stage_next
+            self._stage_next ^= 1
+            g_buf, s_buf = self._stage[slot]
+            copied = torch.cuda.Event()
             with torch.cuda.stream(self._copy_stream):
-                if i >= 2:
-                    self._copy_stream.wait_event(consumed[i % 2])
-                else:
-                    self._copy_stream.wait_stream(main)
+                if self._stage_consumed[slot] is not None:
+                    self._copy_stream.wait_event(self._stage_consumed[slot])
                 g_buf[: hi - lo].copy_(gt_host[lo:hi], non_blocking=True)
                 s_buf[: hi - lo].copy_(sr_host[lo:hi], non_blocking=True)
-                copied[i % 2].record(self._copy_stream)
-            main.wait_event(copied[i % 2])
+                copied.record(self._copy_stream)
+            main.wait_event(copied)
             out_dev[lo:hi] = self._run(g_buf[: hi - lo], s_buf[: hi - lo], head_w, head_b)[0]
-            consumed[i % 2].record(main)
+            consumed = torch.cuda.Event()
+            consumed.record(main)
+            self._stage_consumed[slot] = consumed
         out_host.copy_(out_dev, non_blocking=True)
-        main.synchronize()
-        return out_host
+        done.record(main)
+        if wait:
+            done.synchronize()
+            return out_host
+        return out_host, done
 
 
 class CLIP_lpips_stages_cnn(_B200Scorer):

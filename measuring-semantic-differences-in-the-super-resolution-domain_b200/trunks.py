@@ -131,7 +131,7 @@ def create_trunk(clip_name: str, seed: int = 0) -> nn.Module:
             return timm.create_model(clip_name, pretrained=True)
     except ImportError:
         pass
-    with torch.random.fork_rng():
+    with torch.random.fork_rng(devices=[]):
         torch.manual_seed(seed)
         tree = TREES[family]()
         for m in tree.modules():
@@ -163,6 +163,7 @@ class Program:
         self.ops: list[dict] = []
         self.n_bufs = 0
         self.input_layout = _lib.INPUT_NHWC8
+        self.head_ops = 0   # leading ops (stem + first pool) the plan may run in L2-sized image chunks
 
     def conv(self, conv, bn, src, dst, res=-1, relu=True, cin_pad=None, second=None):
         """One fused conv+BN(+ReLU) op.  `second=(conv1x1, bn, src2)` folds a projection shortcut into the same
@@ -223,6 +224,7 @@ def lower_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Progra
     else:
         P.conv(c1, clip.bn1, IN, T1, cin_pad=8)
     P.pool(_lib.OP_MAXPOOL3S2, T1, A, 3)
+    P.head_ops = len(P.ops)
     x = A
     for li in range(1, 5):
         layer = getattr(clip, f"layer{li}")
@@ -252,6 +254,7 @@ def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> P
     P.conv(st.conv2.conv, st.conv2.bn, T1, T2)
     P.conv(st.conv3.conv, st.conv3.bn, T2, T1)
     P.pool(_lib.OP_AVGPOOL, T1, A, 2)
+    P.head_ops = len(P.ops)
     x = A
     for si, stage in enumerate(clip.stages.children()):
         for bi, blk in enumerate(stage.children()):

@@ -268,7 +268,7 @@ def seeded_init_(model: nn.Module, seed: int = 0, calibrate_bn: bool = True) -> 
 def build_trunk(name: str, seed: int = 0, calibrate_bn: bool = True) -> nn.Module:
     if name not in TRUNKS:
         raise ValueError(f"oracle trunk {name!r} not restated (have {sorted(TRUNKS)})")
-    with torch.random.fork_rng():  # leave the caller's global RNG stream untouched
+    with torch.random.fork_rng(devices=[]):  # leave the caller's global RNG stream untouched
         model = TRUNKS[name]()
         seeded_init_(model, seed, calibrate_bn)
     model.pretrained_cfg = dict(model.default_cfg)

@@ -89,7 +89,7 @@ def test_plan_api_rejects_bad_arguments_without_gpu():
     lib = _lib.load()
     import ctypes as C
     handle = C.c_void_p()
-    assert lib.semdiff_plan_create(None, 0, 0, 0, 0, C.byref(handle)) == -1
+    assert lib.semdiff_plan_create(None, 0, 0, 0, 0, 0, C.byref(handle)) == -1
     assert b"bad arguments" in lib.semdiff_last_error()
     assert lib.semdiff_distance_parts(56 * 56, 256) == 25 and lib.semdiff_distance_parts(49, 2048) == 4
     assert lib.semdiff_distance_parts(1, 8) == 1 and lib.semdiff_distance_parts(1024 * 1024, 256) == 64

@@ -183,3 +183,19 @@ def test_other_image_sizes_fp32(size):
     with torch.no_grad():
         got16 = m16(gt.cuda(), sr.cuda()).cpu()
     assert rel_err(got16, ref) < 6e-2
+
+
+@pytest.mark.parametrize("trunk", ["resnet50", "resnet50_clip.openai"])
+def test_head_chunking_is_bit_identical(trunk, monkeypatch):
+    """Running pack -> stem -> pool in L2-sized image chunks (ragged last chunk included) must not change a bit."""
+    gt, sr = make_pairs(5, seed=13)
+    monkeypatch.setenv("SEMDIFF_HEAD_L2_MB", "0")
+    _, plain = oracle_and_module(trunk, 3, "bf16")
+    with torch.no_grad():
+        ref = plain(gt.cuda(), sr.cuda())
+    monkeypatch.setenv("SEMDIFF_HEAD_L2_MB", "12")      # ~3 images per chunk -> 10 images = 3 + 3 + 3 + 1
+    _, chunked = oracle_and_module(trunk, 3, "bf16")
+    with torch.no_grad():
+        got = chunked(gt.cuda(), sr.cuda())
+    assert chunked.plan().last_launches() > plain.plan().last_launches()
+    assert torch.equal(ref, got)
