@@ -43,7 +43,8 @@ enum {
 /* layout of buffer 0 (what the pack kernel makes of the fp32 NCHW images) */
 enum {
   SEMDIFF_INPUT_NHWC8 = 0,    /* [2n, H, W, 8], channels 3..7 zero */
-  SEMDIFF_INPUT_S2D_ROW4 = 1  /* [2n, H/2+3, W/2, 64]: 2x2 space-to-depth row windows for 7x7/2 stems (elementwise.cu) */
+  SEMDIFF_INPUT_S2D_ROW4 = 1, /* [2n, H/2+3, W/2, 64]: 2x2 space-to-depth row windows for 7x7/2 pad-3 stems (elementwise.cu) */
+  SEMDIFF_INPUT_S2D_ROW2 = 2  /* [2n, H/2+1, W/2, 64]: the same for 3x3/2 pad-1 stems (window of 2, upper 32 channels zero) */
 };
 
 /* One step of the trunk program.  Buffers are logical ids in [0, n_bufs); buffer 0 is the packed

@@ -14,7 +14,7 @@ PRECISIONS = {"bf16": BF16, "fp16": FP16, "fp32": FP32}
 CONV_AUTO, CONV_SIMT, CONV_TC_GATHER, CONV_TC_TMA = 0, 1, 2, 3
 OP_CONV, OP_MAXPOOL3S2, OP_AVGPOOL, OP_TAP = 0, 1, 2, 3
 MAX_PARTS = 64
-INPUT_NHWC8, INPUT_S2D_ROW4 = 0, 1
+INPUT_NHWC8, INPUT_S2D_ROW4, INPUT_S2D_ROW2 = 0, 1, 2
 
 
 class SemdiffOp(C.Structure):

@@ -34,10 +34,13 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ gt,
 // i.e. a 2x2 space-to-depth of the image with the four horizontally adjacent s2d pixels of each output column
 // laid side by side (64 "channels" = one 128-byte row), so the implicit GEMM runs with K = 4 x 64 instead of the
 // 49 x 8 a channel-padded 7x7 window would need.  One thread per (img, i, q, j): 6 float2 reads, 32 bytes written.
+// The same kernel serves SEMDIFF_INPUT_S2D_ROW2 (3x3 stride-2 pad-1 stems, CLIP): window of 2 s2d pixels starting one
+// to the left, one padding row on top (i -> y = 2*(i-1)+dy), slots j = 2, 3 zero (so the row is still 64 wide).
 template <typename T>
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ gt, const float* __restrict__ sr,
-                                                       int n_pairs, int img0, int H, int W, T* __restrict__ out) {
-  const int H2 = H / 2 + 3, W2 = W / 2;
+                                                       int n_pairs, int img0, int H, int W, T* __restrict__ out,
+                                                       int j_real, int off) {
+  const int H2 = H / 2 + (j_real == 4 ? 3 : 1), W2 = W / 2;
   const int per_img = H2 * W2 * 4;
   const int img = img0 + blockIdx.y;
   const int plane = H * W;
@@ -47,11 +50,11 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__
     const int j = t & 3;
     const int r = t >> 2;
     const int i = r / W2, q = r - i * W2;
-    const int y0 = 2 * (i - 2), x0 = 2 * (q - 2 + j);
+    const int y0 = 2 * (i - off), x0 = 2 * (q - off + j);
     float f[16];
 #pragma unroll
     for (int k = 0; k < 16; ++k) f[k] = 0.f;
-    if (x0 >= 0 && x0 < W) {
+    if (j < j_real && x0 >= 0 && x0 < W) {
 #pragma unroll
       for (int dy = 0; dy < 2; ++dy) {
         const int y = y0 + dy;
@@ -199,10 +202,11 @@ static int grid_for(int64_t total, int block) {
 template <typename T>
 static int pack_t(const float* gt, const float* sr, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
                   int layout, cudaStream_t st) {
-  if (layout == SEMDIFF_INPUT_S2D_ROW4) {
-    const int per_img = (H / 2 + 3) * (W / 2) * 4;
+  if (layout == SEMDIFF_INPUT_S2D_ROW4 || layout == SEMDIFF_INPUT_S2D_ROW2) {
+    const bool row4 = layout == SEMDIFF_INPUT_S2D_ROW4;
+    const int per_img = (H / 2 + (row4 ? 3 : 1)) * (W / 2) * 4;
     dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)n_imgs);
-    pack_s2d_kernel<T><<<grid, 256, 0, st>>>(gt, sr, n_pairs, img0, H, W, (T*)out);
+    pack_s2d_kernel<T><<<grid, 256, 0, st>>>(gt, sr, n_pairs, img0, H, W, (T*)out, row4 ? 4 : 2, row4 ? 2 : 1);
   } else {
     const int64_t total = (int64_t)n_imgs * H * W;
     pack_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, img0, n_imgs, H * W, (T*)out);
@@ -216,8 +220,8 @@ int launch_pack(const float* gt, const float* sr, int n_pairs, int img0, int n_i
     set_error("pack: bad shape");
     return SEMDIFF_ERR_ARG;
   }
-  if (layout == SEMDIFF_INPUT_S2D_ROW4 && ((H | W) & 1)) { set_error("pack: the s2d stem layout needs even H and W"); return SEMDIFF_ERR_ARG; }
-  if (layout != SEMDIFF_INPUT_NHWC8 && layout != SEMDIFF_INPUT_S2D_ROW4) { set_error("pack: bad layout %d", layout); return SEMDIFF_ERR_ARG; }
+  if (layout != SEMDIFF_INPUT_NHWC8 && ((H | W) & 1)) { set_error("pack: the s2d stem layouts need even H and W"); return SEMDIFF_ERR_ARG; }
+  if (layout < SEMDIFF_INPUT_NHWC8 || layout > SEMDIFF_INPUT_S2D_ROW2) { set_error("pack: bad layout %d", layout); return SEMDIFF_ERR_ARG; }
   switch (precision) {
     case SEMDIFF_BF16: return pack_t<__nv_bfloat16>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
     case SEMDIFF_FP16: return pack_t<__half>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);

@@ -68,9 +68,9 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
   std::vector<BufShape> cur(P->n_bufs);
   std::vector<int64_t> buf_elems(P->n_bufs, 0);
   const int64_t n_img = 2 * (int64_t)pairs;
-  if (P->input_layout == SEMDIFF_INPUT_S2D_ROW4) {
-    if ((H | W) & 1) { set_error("the s2d stem layout needs even H and W (got %dx%d)", H, W); return SEMDIFF_ERR_ARG; }
-    cur[0] = BufShape{H / 2 + 3, W / 2, 64};
+  if (P->input_layout != SEMDIFF_INPUT_NHWC8) {
+    if ((H | W) & 1) { set_error("the s2d stem layouts need even H and W (got %dx%d)", H, W); return SEMDIFF_ERR_ARG; }
+    cur[0] = BufShape{H / 2 + (P->input_layout == SEMDIFF_INPUT_S2D_ROW4 ? 3 : 1), W / 2, 64};
   } else {
     cur[0] = BufShape{H, W, 8};
   }
@@ -235,7 +235,7 @@ int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, in
                         int32_t head_ops, semdiff_plan** out) {
   if (ops == nullptr || out == nullptr || n_ops <= 0 || n_bufs < 2) { set_error("plan_create: bad arguments"); return SEMDIFF_ERR_ARG; }
   if (precision < SEMDIFF_BF16 || precision > SEMDIFF_FP32) { set_error("plan_create: bad precision %d", precision); return SEMDIFF_ERR_ARG; }
-  if (input_layout != SEMDIFF_INPUT_NHWC8 && input_layout != SEMDIFF_INPUT_S2D_ROW4) { set_error("plan_create: bad input layout %d", input_layout); return SEMDIFF_ERR_ARG; }
+  if (input_layout < SEMDIFF_INPUT_NHWC8 || input_layout > SEMDIFF_INPUT_S2D_ROW2) { set_error("plan_create: bad input layout %d", input_layout); return SEMDIFF_ERR_ARG; }
   semdiff_plan* P = new semdiff_plan();
   P->input_layout = input_layout;
   P->head_ops = head_ops < 0 || head_ops > n_ops ? 0 : head_ops;

@@ -165,15 +165,19 @@ class Program:
         self.input_layout = _lib.INPUT_NHWC8
         self.head_ops = 0   # leading ops (stem + first pool) the plan may run in L2-sized image chunks
 
-    def conv(self, conv, bn, src, dst, res=-1, relu=True, cin_pad=None, second=None):
+    def conv(self, conv, bn, src, dst, res=-1, relu=True, cin_pad=None, second=None, cout_pad=None):
         """One fused conv+BN(+ReLU) op.  `second=(conv1x1, bn, src2)` folds a projection shortcut into the same
         launch: its (folded) weights are appended along K and the kernel reads `src2` for those K columns, so
         out = act(conv(src) + conv1x1(src2) + b + b2) never materialises the shortcut tensor."""
         w, b = fold_conv_bn(conv, bn, cin_pad)
+        if cout_pad is not None and cout_pad > w.shape[0]:   # zero filters: the extra output channels are exactly 0
+            w = torch.cat([w, torch.zeros(cout_pad - w.shape[0], *w.shape[1:], dtype=w.dtype)])
+            b = torch.cat([b, torch.zeros(cout_pad - b.shape[0], dtype=b.dtype)])
         op = dict(kind=_lib.OP_CONV, src=src, dst=dst, res=res, cin=w.shape[3], cout=w.shape[0],
                   kh=w.shape[1], kw=w.shape[2], stride=conv.stride[0], pad=conv.padding[0],
                   relu=int(relu), tap=-1, src2=-1, cin2=0, stride2=1,
-                  alg_k=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1], n_convs=1)
+                  alg_k=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1], alg_cout=conv.out_channels,
+                  n_convs=1)
         w = w.reshape(w.shape[0], -1)
         if second is not None:
             conv2, bn2, src2 = second
@@ -201,7 +205,7 @@ class Program:
         self.input_layout = _lib.INPUT_S2D_ROW4
         self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=-1, cin=64, cout=w.shape[0], kh=4, kw=1, stride=1,
                              pad=0, relu=1, tap=-1, src2=-1, cin2=0, stride2=1, w=w2.reshape(w2.shape[0], -1).contiguous(),
-                             b=b, alg_k=147, n_convs=1))
+                             b=b, alg_k=147, alg_cout=w.shape[0], n_convs=1))
 
     def pool(self, kind, src, dst, window):
         self.ops.append(dict(kind=kind, src=src, dst=dst, res=-1, cin=0, cout=0, kh=window, kw=window, stride=window,
@@ -210,6 +214,26 @@ class Program:
     def tap(self, src, j):
         self.ops.append(dict(kind=_lib.OP_TAP, src=src, dst=-1, res=-1, cin=0, cout=0, kh=0, kw=0, stride=0, pad=0,
                              relu=0, tap=j, src2=-1, cin2=0, stride2=1, w=None, b=None))
+
+
+    def stem3_s2d(self, conv, bn, src, dst, cout_pad=64):
+        """3x3 stride-2 pad-1 stem (CLIP) as a 2x1 stride-1 conv over the SEMDIFF_INPUT_S2D_ROW2 buffer:
+        ky -> (row r = (ky+1)//2, dy = (ky+1)%2), kx -> (window pixel j = (kx+1)//2, dx = (kx+1)%2)."""
+        w, b = fold_conv_bn(conv, bn)                      # [Cout, 3, 3, 3]
+        cout = max(w.shape[0], cout_pad)
+        w2 = torch.zeros(cout, 2, 1, 64, dtype=w.dtype)
+        for ky in range(3):
+            r, dy = (ky + 1) // 2, (ky + 1) % 2
+            for kx in range(3):
+                j, dx = (kx + 1) // 2, (kx + 1) % 2
+                base = j * 16 + (dy * 2 + dx) * 3
+                w2[:w.shape[0], r, 0, base:base + 3] = w[:, ky, kx, :]
+        b2 = torch.zeros(cout, dtype=b.dtype)
+        b2[:b.shape[0]] = b
+        self.input_layout = _lib.INPUT_S2D_ROW2
+        self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=-1, cin=64, cout=cout, kh=2, kw=1, stride=1,
+                             pad=0, relu=1, tap=-1, src2=-1, cin2=0, stride2=1, w=w2.reshape(cout, -1).contiguous(),
+                             b=b2, alg_k=27, alg_cout=w.shape[0], n_convs=1))
 
 
 def lower_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Program:
@@ -250,9 +274,17 @@ def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> P
     IN, A, B, T1, T2, T3, D0 = range(7)
     P.n_bufs = 7
     st = clip.stem
-    P.conv(st.conv1.conv, st.conv1.bn, IN, T1, cin_pad=8)
-    P.conv(st.conv2.conv, st.conv2.bn, T1, T2)
-    P.conv(st.conv3.conv, st.conv3.bn, T2, T1)
+    c1 = st.conv1.conv
+    if s2d_stem and c1.kernel_size == (3, 3) and c1.stride == (2, 2) and c1.padding == (1, 1) and c1.in_channels == 3:
+        # 32-channel stem activations are carried as 64 channels (upper half exactly zero) so that every stem conv
+        # runs on the TMA-im2col tensor-core path (64 channels = one 128-byte swizzle row)
+        P.stem3_s2d(c1, st.conv1.bn, IN, T1, cout_pad=64)
+        P.conv(st.conv2.conv, st.conv2.bn, T1, T2, cin_pad=64, cout_pad=64)
+        P.conv(st.conv3.conv, st.conv3.bn, T2, T1, cin_pad=64)
+    else:
+        P.conv(c1, st.conv1.bn, IN, T1, cin_pad=8)
+        P.conv(st.conv2.conv, st.conv2.bn, T1, T2)
+        P.conv(st.conv3.conv, st.conv3.bn, T2, T1)
     P.pool(_lib.OP_AVGPOOL, T1, A, 2)
     P.head_ops = len(P.ops)
     x = A
@@ -286,14 +318,15 @@ LOWER = {"resnet50": lower_resnet50, "resnet50_clip.openai": lower_clip_resnet50
 
 def conv_flops(program: Program, H: int, W: int) -> int:
     """Algorithmic FLOPs (2*MAC, unpadded Cin) of the conv ops for ONE HxW image."""
-    shapes = {0: (H // 2 + 3, W // 2) if program.input_layout == _lib.INPUT_S2D_ROW4 else (H, W)}
+    pad_rows = {_lib.INPUT_S2D_ROW4: 3, _lib.INPUT_S2D_ROW2: 1}.get(program.input_layout)
+    shapes = {0: (H // 2 + pad_rows, W // 2) if pad_rows else (H, W)}
     total = 0
     for op in program.ops:
         h, w = shapes[op["src"]]
         if op["kind"] == _lib.OP_CONV:
             oh = (h + 2 * op["pad"] - op["kh"]) // op["stride"] + 1
             ow = (w + 2 * op["pad"] - op["kw"]) // op["stride"] + 1
-            total += 2 * oh * ow * op["cout"] * op["alg_k"]
+            total += 2 * oh * ow * op["alg_cout"] * op["alg_k"]
             shapes[op["dst"]] = (oh, ow)
         elif op["kind"] == _lib.OP_MAXPOOL3S2:
             shapes[op["dst"]] = ((h - 1) // 2 + 1, (w - 1) // 2 + 1)

@@ -120,3 +120,33 @@ def test_s2d_stem_weights_reproduce_the_7x7_conv():
     got = torch.nn.functional.conv2d(X2.permute(0, 3, 1, 2), op["w"].reshape(64, 4, 1, 64).permute(0, 3, 1, 2), op["b"])
     ref = tree.bn1.double().eval()(tree.conv1.double()(x))
     assert got.shape == ref.shape and torch.allclose(got, ref, rtol=1e-10, atol=1e-10)
+
+
+def test_clip_s2d_stem_weights_reproduce_the_3x3_stride2_conv():
+    torch.manual_seed(1)
+    tree = trunks.create_trunk("resnet50_clip.openai")
+    bn = tree.stem.conv1.bn
+    with torch.no_grad():
+        bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0); bn.bias.normal_()
+    prog = trunks.lower_clip_resnet50(tree, 0)
+    assert prog.input_layout == _lib.INPUT_S2D_ROW2 and prog.head_ops == 4
+    op = prog.ops[0]
+    assert (op["kh"], op["kw"], op["cin"], op["cout"], op["alg_k"]) == (2, 1, 64, 64, 27)
+    H, W = 12, 16
+    x = torch.randn(2, 3, H, W, dtype=torch.double)
+    X2 = torch.zeros(2, H // 2 + 1, W // 2, 64, dtype=torch.double)
+    for i in range(H // 2 + 1):
+        for q in range(W // 2):
+            for j in range(2):
+                for dy in range(2):
+                    for dx in range(2):
+                        y, xx = 2 * (i - 1) + dy, 2 * (q - 1 + j) + dx
+                        if 0 <= y < H and 0 <= xx < W:
+                            c = j * 16 + (dy * 2 + dx) * 3
+                            X2[:, i, q, c:c + 3] = x[:, :, y, xx]
+    got = torch.nn.functional.conv2d(X2.permute(0, 3, 1, 2), op["w"].reshape(64, 2, 1, 64).permute(0, 3, 1, 2), op["b"])
+    ref = bn.double().eval()(tree.stem.conv1.conv.double()(x))
+    assert got.shape[1] == 64 and torch.allclose(got[:, :32], ref, rtol=1e-10, atol=1e-10)
+    assert torch.count_nonzero(got[:, 32:]) == 0
+    # the padded 64-channel stem chain: conv2 / conv3 ignore the zero half
+    assert prog.ops[1]["cin"] == 64 and prog.ops[1]["cout"] == 64 and prog.ops[2]["cin"] == 64 and prog.ops[2]["cout"] == 64

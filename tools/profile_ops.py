@@ -56,7 +56,7 @@ def main():
             ms, cnt = plan.profile(reset=True)
             plan.set_profiling(False)
         ops = plan.program.ops
-        shapes = {0: (S // 2 + 3, S // 2, 64) if plan.program.input_layout == 1 else (S, S, 8)}
+        shapes = {0: {1: (S // 2 + 3, S // 2, 64), 2: (S // 2 + 1, S // 2, 64)}.get(plan.program.input_layout, (S, S, 8))}
         rows, tot_conv, tot_flop = [], 0.0, 0.0
         eb = 4 if args.precision == "fp32" else 2
         for i, op in enumerate(ops):
@@ -66,7 +66,7 @@ def main():
                 oh = (h + 2 * op["pad"] - op["kh"]) // op["stride"] + 1
                 ow = (w + 2 * op["pad"] - op["kw"]) // op["stride"] + 1
                 shapes[op["dst"]] = (oh, ow, op["cout"])
-                fl = 2.0 * oh * ow * op["cout"] * op["alg_k"] * 2 * n
+                fl = 2.0 * oh * ow * op["alg_cout"] * op["alg_k"] * 2 * n
                 by = (h * w * c + oh * ow * op["cout"] * (2 if op["res"] >= 0 else 1)) * eb * 2 * n
                 rows.append((i, f"conv {op['kh']}x{op['kw']}s{op['stride']} {c}->{op['cout']} @{h}", t, fl / t / 1e9 if t else 0, by / t / 1e6 if t else 0))
                 tot_conv += t
