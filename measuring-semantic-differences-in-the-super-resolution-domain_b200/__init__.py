@@ -2,6 +2,6 @@
 /root/reference/models/global_eval_models.py's CLIP_lpips_stages_cnn / CLIP_lpips_stages_cnn_clsbckb.
 Import as `semdiff_b200` (alias module at the repo root; this directory's name is not a Python identifier)."""
 from . import _lib, trunks  # noqa: F401
-from .global_eval_models import CLIP_lpips_stages_cnn, CLIP_lpips_stages_cnn_clsbckb  # noqa: F401
+from .global_eval_models import CLIP_lpips_stages_cnn, CLIP_lpips_stages_cnn_clsbckb, CLIP_lpips_wperlay_cnn  # noqa: F401
 
-__all__ = ["CLIP_lpips_stages_cnn", "CLIP_lpips_stages_cnn_clsbckb", "trunks"]
+__all__ = ["CLIP_lpips_stages_cnn", "CLIP_lpips_stages_cnn_clsbckb", "CLIP_lpips_wperlay_cnn", "trunks"]

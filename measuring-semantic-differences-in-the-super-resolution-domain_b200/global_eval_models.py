@@ -33,11 +33,11 @@ class _Plan:
     """Device-resident folded weights + the native plan handle.  Rebuilt when trunk weights change."""
 
     def __init__(self, clip: nn.Module, family: str, depth: int, precision: str, device: torch.device,
-                 s2d_stem: bool = True):
+                 s2d_stem: bool = True, lower_kwargs: dict | None = None):
         self.lib = _lib.load()
         self.precision = _lib.PRECISIONS[precision]
         dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[precision]
-        self.program = trunks.LOWER[family](clip, depth, s2d_stem)
+        self.program = trunks.LOWER[family](clip, depth, s2d_stem, **(lower_kwargs or {}))
         ops = self.program.ops
         self._keep = []
         arr = (_lib.SemdiffOp * len(ops))()
@@ -111,7 +111,13 @@ class _ScoreFn(torch.autograd.Function):
 
 
 class _B200Scorer(nn.Module):
-    _DEFAULT_TRUNK = None  # set by subclasses; only used for the tap-name pattern
+    _MAX_DEPTH = 3   # w_layers = Conv2d(256 * 2**s, 1, 1) for s in range(3-depth, 4)  (:336)
+
+    def _tap_channels(self, depth):
+        return [256 * (2 ** s) for s in range(3 - depth, 4)]
+
+    def _lower_kwargs(self):
+        return None
 
     def __init__(self, clip_name: str, depth: int, device: str, enc_ft: bool = False, *, precision: str = "bf16",
                  microbatch: int | None = None, normalize: bool = False):
@@ -120,8 +126,8 @@ class _B200Scorer(nn.Module):
             raise NotImplementedError(
                 "enc_ft=True (fine-tuning the trunk through autograd) is not supported by the B200 scorer: the trunk "
                 "is an inference-only kernel program with folded BatchNorm")
-        if not (0 <= int(depth) <= 3):
-            raise ValueError("depth must be in 0..3 (w_layers = Conv2d(256 * 2**s, 1, 1) for s in range(3-depth, 4))")
+        if not (0 <= int(depth) <= self._MAX_DEPTH):
+            raise ValueError(f"depth must be in 0..{self._MAX_DEPTH}")
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
         dev = torch.device(device)
@@ -138,7 +144,7 @@ class _B200Scorer(nn.Module):
         print(self.wanted_layers)  # the reference prints this too (:328 / :702)
         cfg = getattr(self.clip, "pretrained_cfg", None) or {}
         self.processor = make_processor(dict(cfg))
-        self.w_layers = nn.ModuleList([nn.Conv2d(256 * (2 ** s), 1, kernel_size=1, stride=1) for s in range(3 - depth, 4)])
+        self.w_layers = nn.ModuleList([nn.Conv2d(c, 1, kernel_size=1, stride=1) for c in self._tap_channels(depth)])
         self.final_relu = nn.ReLU()
         self.w_layers.to(dev)
         self.precision, self.microbatch, self.normalize = precision, microbatch, normalize
@@ -197,7 +203,8 @@ class _B200Scorer(nn.Module):
             dev = next(self.w_layers.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("the module was moved off the GPU; the B200 scorer has no CPU fallback")
-            self._plan[even_size] = _Plan(self.clip, self.family, self.depth, self.precision, dev, s2d_stem=even_size)
+            self._plan[even_size] = _Plan(self.clip, self.family, self.depth, self.precision, dev, s2d_stem=even_size,
+                                          lower_kwargs=self._lower_kwargs())
         return self._plan[even_size]
 
     def default_microbatch(self, H: int, W: int) -> int:
@@ -301,3 +308,23 @@ class CLIP_lpips_stages_cnn_clsbckb(_B200Scorer):
         if self.family != "resnet50":
             raise ValueError("CLIP_lpips_stages_cnn_clsbckb hooks `layer{s}.2.act3`; use a resnet50 trunk (reference :701)")
         return [f"layer{s}.2.act3" for s in range(4 - depth, 5)]
+
+
+class CLIP_lpips_wperlay_cnn(_B200Scorer):
+    """timm `resnet50_clip.openai` trunk, one weight layer per block output: taps are the last depth+1 of
+    stages.{s}.{0,1,2}.act (reference :815-914; hook list :832-833, w_layers :845-847).  depth in 0..11."""
+    _MAX_DEPTH = 11
+
+    def _all_taps(self):
+        return [(s, lay) for s in range(4) for lay in range(3)]
+
+    def _tap_names(self, depth):
+        if self.family != "resnet50_clip.openai":
+            raise ValueError("CLIP_lpips_wperlay_cnn hooks `stages.{s}.{lay}.act`; use a resnet50_clip.* trunk (reference :832)")
+        return [f"stages.{s}.{lay}.act" for s, lay in self._all_taps()][11 - depth:]
+
+    def _tap_channels(self, depth):
+        return [256 * (2 ** s) for s, _ in self._all_taps()[11 - depth:]]
+
+    def _lower_kwargs(self):
+        return {"taps": {sl: j for j, sl in enumerate(self._all_taps()[11 - self.depth:])}}

@@ -268,8 +268,11 @@ def lower_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Progra
     return P
 
 
-def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Program:
-    """timm resnet50_clip.openai; taps = stages.{s}.2.act for s in range(3-depth, 4)  (global_eval_models.py:327)."""
+def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True, taps: dict | None = None) -> Program:
+    """timm resnet50_clip.openai; taps = stages.{s}.2.act for s in range(3-depth, 4)  (global_eval_models.py:327),
+    or an explicit {(stage, block): tap index} map (CLIP_lpips_wperlay_cnn, :832-833)."""
+    if taps is None:
+        taps = {(s, 2): s - (3 - depth) for s in range(3 - depth, 4)}
     P = Program()
     IN, A, B, T1, T2, T3, D0 = range(7)
     P.n_bufs = 7
@@ -308,8 +311,8 @@ def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> P
             else:
                 P.conv(blk.conv3_1x1.conv, blk.conv3_1x1.bn, mid, y, res=x)
             x = y
-            if bi == 2 and si >= 3 - depth:
-                P.tap(x, si - (3 - depth))
+            if (si, bi) in taps:
+                P.tap(x, taps[(si, bi)])
     return P
 
 

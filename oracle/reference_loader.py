@@ -43,7 +43,8 @@ def load_reference_module():
     return mod
 
 
-def build_reference_scorer(trunk: str, depth: int, seed: int = 0, calibrate_bn: bool = True, quiet: bool = True):
+def build_reference_scorer(trunk: str, depth: int, seed: int = 0, calibrate_bn: bool = True, quiet: bool = True,
+                           variant: str = "stages"):
     """Instantiate the reference class for `trunk` on CPU with the seeded oracle trunk.
     resnet50 -> CLIP_lpips_stages_cnn_clsbckb (:682), resnet50_clip.openai -> CLIP_lpips_stages_cnn (:308)."""
     import torch
@@ -52,6 +53,8 @@ def build_reference_scorer(trunk: str, depth: int, seed: int = 0, calibrate_bn: 
     import timm  # the shim (on sys.path after load_reference_module)
     timm.SEED, timm.CALIBRATE_BN = seed, calibrate_bn
     cls = mod.CLIP_lpips_stages_cnn_clsbckb if trunk == "resnet50" else mod.CLIP_lpips_stages_cnn
+    if variant == "wperlay":
+        cls = mod.CLIP_lpips_wperlay_cnn  # :815
     torch.manual_seed(seed + 1000)  # seeds the reference's own default init of w_layers (:336)
     with (contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()):
         model = cls(clip_name=trunk, depth=depth, device="cpu")

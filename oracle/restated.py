@@ -15,22 +15,27 @@ import torch.nn as nn
 from .trunks import build_trunk
 
 
-def tap_names(trunk: str, depth: int):
+def tap_names(trunk: str, depth: int, variant: str = "stages"):
+    if variant == "wperlay":                                            # :832-833
+        return [f"stages.{s}.{lay}.act" for s in range(4) for lay in range(3)][11 - depth:]
     if trunk == "resnet50":
         return [f"layer{s}.2.act3" for s in range(4 - depth, 5)]      # :701
     return [f"stages.{s}.2.act" for s in range(3 - depth, 4)]          # :327
 
 
 class RestatedScorer(nn.Module):
-    def __init__(self, trunk: str, depth: int, seed: int = 0, calibrate_bn: bool = True):
+    def __init__(self, trunk: str, depth: int, seed: int = 0, calibrate_bn: bool = True, variant: str = "stages"):
         super().__init__()
         self.clip = build_trunk(trunk, seed=seed, calibrate_bn=calibrate_bn)
         self.depth = depth
         self.trunk_name = trunk
-        self.wanted_layers = tap_names(trunk, depth)
+        self.wanted_layers = tap_names(trunk, depth, variant)
         torch.manual_seed(seed + 1000)  # same stream as reference_loader.build_reference_scorer
-        self.w_layers = nn.ModuleList(
-            [nn.Conv2d(256 * (2 ** s), 1, kernel_size=1, stride=1) for s in range(3 - depth, 4)])  # :336
+        if variant == "wperlay":   # :841-847: one Conv2d(256 * 2**stage, 1, 1) per hooked block
+            chans = [256 * (2 ** int(name.split(".")[1])) for name in self.wanted_layers]
+        else:                      # :336
+            chans = [256 * (2 ** s) for s in range(3 - depth, 4)]
+        self.w_layers = nn.ModuleList([nn.Conv2d(c, 1, kernel_size=1, stride=1) for c in chans])
         self._taps = {}
         mods = dict(self.clip.named_modules())
         for name in self.wanted_layers:

@@ -54,3 +54,14 @@ def test_tap_shapes_and_depths():
     assert [tuple(f.shape) for f in feats] == [(1, 256, 56, 56), (1, 512, 28, 28), (1, 1024, 14, 14), (1, 2048, 7, 7)]
     for depth in range(4):
         assert len(tap_names("resnet50", depth)) == depth + 1 == len(tap_names("resnet50_clip.openai", depth))
+
+
+@pytest.mark.skipif(not rl.available(), reason="/root/reference not present on this host")
+def test_restated_wperlay_equals_reference_file():
+    ref = set_head(rl.build_reference_scorer("resnet50_clip.openai", 5, seed=0, variant="wperlay"), "abs")
+    mine = set_head(RestatedScorer("resnet50_clip.openai", 5, seed=0, variant="wperlay"), "abs")
+    assert ref.wanted_layers == mine.wanted_layers and len(mine.w_layers) == 6
+    assert [m.in_channels for m in ref.w_layers] == [m.in_channels for m in mine.w_layers] == [1024] * 3 + [2048] * 3
+    gt, sr = make_pairs(2, seed=5)
+    with torch.no_grad():
+        assert torch.equal(ref(gt, sr), mine(gt, sr))

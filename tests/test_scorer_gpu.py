@@ -217,3 +217,18 @@ def test_rank_order_16bit_vs_fp32_mode():
     rho32, rho16, rhoh = (spearmanr(ref.numpy(), s.numpy())[0] for s in (s32, s16, sh))
     print(f"[rank] spearman vs oracle over 96 pairs: fp32 {rho32:.6f} fp16 {rhoh:.6f} bf16 {rho16:.6f}")
     assert rho32 > 0.99999 and rhoh > 0.9995 and rho16 > 0.995
+
+
+@pytest.mark.parametrize("depth", [11, 4])
+def test_wperlay_variant(depth):
+    """CLIP_lpips_wperlay_cnn (reference :815-914): up to 12 taps, one per block output."""
+    oracle = set_head(RestatedScorer("resnet50_clip.openai", depth, seed=0, variant="wperlay"), "abs")
+    gt, sr = make_pairs(3, seed=17)
+    ref = oracle(gt, sr)
+    for precision, tol in (("fp32", 1e-5), ("bf16", 6e-2)):
+        model = semdiff_b200.CLIP_lpips_wperlay_cnn("resnet50_clip.openai", depth, "cuda", precision=precision)
+        assert model.wanted_layers == oracle.wanted_layers
+        model.load_state_dict(oracle.state_dict(), strict=True)
+        with torch.no_grad():
+            got = model(gt.cuda(), sr.cuda()).cpu()
+        assert rel_err(got, ref) < tol, (precision, got, ref)
