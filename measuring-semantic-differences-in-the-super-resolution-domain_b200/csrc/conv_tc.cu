@@ -12,8 +12,9 @@
 //                 A_TMA     1x1 stride-1 convs: plain 2-D tiled loads of [M, Cin]
 //                 A_IM2COL  kxk / strided convs with Cin % 64 == 0: TMA im2col mode over the NHWC tensor
 //   warp 1      tcgen05.mma issuer (one thread); owns the TMEM allocation (2 accumulator stages)
-//   warps 2-5   epilogue: tcgen05.ld -> +bias (+residual) -> ReLU -> 16-bit -> swizzled smem -> TMA store
-//   warp 6      residual loader: TMA-prefetches the residual tile into the smem slot the epilogue will
+//   warps 2-9   epilogue (8 warps = 4 TMEM lane quarters x 2 column halves; 4 warps in the gather variant):
+//               tcgen05.ld -> +bias (+residual) -> ReLU -> 16-bit -> swizzled smem -> TMA store
+//   warp 10     residual loader: TMA-prefetches the residual tile into the smem slot the epilogue will
 //               overwrite in place with the result (ring of slots, freed when the store has read them)
 //   warps 6-9   (A_GATHER only; the residual loader is then warp 10) software im2col for Cin < 64 (stems): cp.async 16 B chunks into the swizzled
 //               A tile, zero-filling padding / M tail / K tail
@@ -69,9 +70,16 @@ template <int ROW_BYTES> __device__ __forceinline__ uint32_t swz_chunk(uint32_t 
   else return chunk ^ ((row >> 1) & 3);
 }
 
+// epilogue warps: 8 (two per TMEM lane quarter, splitting the columns) except where warps 6-9 are the gather producers
+template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int epi_warps() { return (kAMode == A_GATHER || BLOCK_N < 64) ? 4 : 8; }
+template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int cta_threads() {
+  return kAMode == A_GATHER ? 352 : (2 + epi_warps<BLOCK_N, kAMode>() + 1) * 32;
+}
+
 template <typename T, int BLOCK_N, int kAMode>
-__global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
+__global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N>;
+  constexpr int EPI_WARPS = epi_warps<BLOCK_N, kAMode>();
   constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);
+      mbar_init(&tmem_empty_bar[i], EPI_WARPS);
     }
     for (int i = 0; i < RING; ++i) {
       mbar_init(&res_full_bar[i], 1);
@@ -187,10 +195,13 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp < 6) {
-    // ===================== epilogue =====================
+  } else if (warp < 2 + EPI_WARPS) {
+    // ===================== epilogue (EPI_WARPS warps: 4 TMEM lane quarters x HALVES column halves) =====================
     constexpr int ROW_BYTES = Cfg::BOX_COLS * 2;
-    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    constexpr int HALVES = EPI_WARPS / 4;
+    constexpr int UNITS = Cfg::GROUP_COLS / 32;          // 32-column units per group (one tcgen05.ld.x32 each)
+    const int q = warp & 3;                              // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const bool store_thread = (warp == 2 && leader);
     int local = 0, gc = 0;  // gc: running column-group counter of this CTA (ring position)
@@ -206,7 +217,7 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
           mbar_wait(&res_full_bar[slot], (gc / RING) & 1);  // residual landed (and the slot is ours)
         } else {
           if (store_thread) bulk_wait_read<RING - 1>();      // the store that last used this slot has read it
-          named_bar_sync(1, 128);
+          named_bar_sync(1, EPI_WARPS * 32);
         }
         if (!tmem_ready) {
           mbar_wait(&tmem_full_bar[acc], acc_phase);
@@ -214,31 +225,30 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
           tmem_ready = true;
         }
 #pragma unroll 1
-        for (int b = 0; b < Cfg::BOXES; ++b) {
-          const int col_in_tile = g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS;
-          uint32_t v[Cfg::BOX_COLS];
-          const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + col_in_tile;
-#pragma unroll
-          for (int h = 0; h < Cfg::BOX_COLS / 32; ++h)
-            tmem_ld_32x32b_x32(taddr + h * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[h * 32]));
+        for (int u = half; u < UNITS; u += HALVES) {
+          const int col_in_group = u * 32;
+          const int col_in_tile = g * Cfg::GROUP_COLS + col_in_group;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N + col_in_tile, v);
           tmem_ld_wait();
-          if (g == Cfg::GROUPS - 1 && b == Cfg::BOXES - 1) {
-            // every TMEM read of this accumulator stage has retired: hand it back to the MMA warp early
+          if (g == Cfg::GROUPS - 1 && u + HALVES >= UNITS) {
+            // this warp's last TMEM read of the accumulator stage has retired: hand it back to the MMA warp early
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
           const int col0 = n_tile * BLOCK_N + col_in_tile;
-          const uint32_t row_addr = smem_u32(cbuf + b * Cfg::BOX_BYTES) + row * ROW_BYTES;
+          const int box = col_in_group / Cfg::BOX_COLS, j0 = (col_in_group % Cfg::BOX_COLS) / 8;
+          const uint32_t row_addr = smem_u32(cbuf + box * Cfg::BOX_BYTES) + row * ROW_BYTES;
 #pragma unroll
-          for (int j = 0; j < Cfg::BOX_COLS / 8; ++j) {
+          for (int j = 0; j < 4; ++j) {
             const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
             const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
             float f[8] = {__uint_as_float(v[j * 8 + 0]) + b0.x, __uint_as_float(v[j * 8 + 1]) + b0.y,
                           __uint_as_float(v[j * 8 + 2]) + b0.z, __uint_as_float(v[j * 8 + 3]) + b0.w,
                           __uint_as_float(v[j * 8 + 4]) + b1.x, __uint_as_float(v[j * 8 + 5]) + b1.y,
                           __uint_as_float(v[j * 8 + 6]) + b1.z, __uint_as_float(v[j * 8 + 7]) + b1.w};
-            const uint32_t addr = row_addr + (swz_chunk<ROW_BYTES>(j, row) << 4);
+            const uint32_t addr = row_addr + (swz_chunk<ROW_BYTES>(j0 + j, row) << 4);
             if (p.has_res) {
               uint4 rq;
               asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rq.x), "=r"(rq.y), "=r"(rq.z), "=r"(rq.w) : "r"(addr));
@@ -256,7 +266,7 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
           }
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store (async proxy)
-        named_bar_sync(1, 128);
+        named_bar_sync(1, EPI_WARPS * 32);
         if (store_thread) {
 #pragma unroll
           for (int b = 0; b < Cfg::BOXES; ++b)
@@ -271,7 +281,7 @@ __global__ void __launch_bounds__(kAMode == A_GATHER ? 352 : 224, 1) conv_tc_ker
       }
     }
     if (store_thread) bulk_wait<0>();  // smem must stay valid until the last store has completed
-  } else if (warp == (kAMode == A_GATHER ? 10 : 6)) {
+  } else if (warp == (kAMode == A_GATHER ? 10 : 2 + EPI_WARPS)) {
     // ===================== residual loader =====================
     if (leader && p.has_res) {
       int gc = 0;
@@ -480,7 +490,7 @@ static int launch_t(const ConvTcParams& p, cudaStream_t st) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, kAMode == A_GATHER ? 352 : 224, Cfg::SMEM_BYTES, st>>>(p);
+  kern<<<grid, cta_threads<BLOCK_N, kAMode>(), Cfg::SMEM_BYTES, st>>>(p);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
