@@ -97,6 +97,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// for warps that may wait long (epilogue waiting for a whole main loop): back off so that the polling does not
+// compete for issue slots with the TMA-producer / MMA-issuer warps that share the SM sub-partition
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t ns = 32;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(ns);
+    if (ns < 256) ns <<= 1;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------
 // proxy fences, cp.async (LDGSTS)

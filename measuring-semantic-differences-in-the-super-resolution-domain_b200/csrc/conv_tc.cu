@@ -71,7 +71,7 @@ template <int ROW_BYTES> __device__ __forceinline__ uint32_t swz_chunk(uint32_t 
 }
 
 // epilogue warps: 8 (two per TMEM lane quarter, splitting the columns) except where warps 6-9 are the gather producers
-template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int epi_warps() { return (kAMode == A_GATHER || BLOCK_N < 64) ? 4 : 8; }
+template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int epi_warps() { return (kAMode == A_GATHER || BLOCK_N <= 64) ? 4 : 8; }
 template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int cta_threads() {
   return kAMode == A_GATHER ? 352 : (2 + epi_warps<BLOCK_N, kAMode>() + 1) * 32;
 }
@@ -214,13 +214,13 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
         const int slot = gc % RING;
         uint8_t* cbuf = smem_c + slot * Cfg::GROUP_BYTES;
         if (p.has_res) {
-          mbar_wait(&res_full_bar[slot], (gc / RING) & 1);  // residual landed (and the slot is ours)
+          mbar_wait_backoff(&res_full_bar[slot], (gc / RING) & 1);  // residual landed (and the slot is ours)
         } else {
           if (store_thread) bulk_wait_read<RING - 1>();      // the store that last used this slot has read it
           named_bar_sync(1, EPI_WARPS * 32);
         }
         if (!tmem_ready) {
-          mbar_wait(&tmem_full_bar[acc], acc_phase);
+          mbar_wait_backoff(&tmem_full_bar[acc], acc_phase);
           tcgen05_fence_after();
           tmem_ready = true;
         }
