@@ -86,7 +86,8 @@ int semdiff_plan_set_conv_impl(semdiff_plan* plan, int32_t impl);
 int64_t semdiff_workspace_bytes(const semdiff_plan* plan, int32_t microbatch_pairs, int32_t H, int32_t W);
 
 /* forward(a, b) -> score, :341-397 / :717-773.
- *   gt, sr        device fp32 NCHW [n_pairs,3,H,W]
+ *   gt, sr        device NCHW [n_pairs,3,H,W]; element type in_precision = SEMDIFF_FP32 (what the reference passes),
+ *                 or SEMDIFF_BF16 / SEMDIFF_FP16 when the caller already holds 16-bit images (halves the PCIe bytes)
  *   head_w        device fp32, w_layers[j].weight concatenated in tap order (sum_j C_j floats)
  *   head_b        device fp32 [n_taps], w_layers[j].bias
  *   out_scores    device fp32 [n_pairs]   = relu(mean_j(b_j + mean_hw sum_c w_j[c] (A-B)^2))
@@ -94,8 +95,8 @@ int64_t semdiff_workspace_bytes(const semdiff_plan* plan, int32_t microbatch_pai
  *   out_chan_mean device fp32 [n_pairs, sum_j C_j] or NULL: per-channel spatial means of (A-B)^2
  *                 (d score / d w_j[c] * n_taps; lets the caller train w_layers, :55-69 of the sweep script)
  * Pairs are processed in micro-batches of `microbatch_pairs` so that activations stay L2-resident. */
-int semdiff_score(semdiff_plan* plan, const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W,
-                  int32_t microbatch_pairs, const float* head_w, const float* head_b, int32_t normalize,
+int semdiff_score(semdiff_plan* plan, const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H,
+                  int32_t W, int32_t microbatch_pairs, const float* head_w, const float* head_b, int32_t normalize,
                   void* workspace, int64_t workspace_bytes, float* out_scores, float* out_pre_relu,
                   float* out_chan_mean, semdiff_stream_t stream);
 
@@ -109,9 +110,9 @@ int64_t semdiff_plan_last_launches(const semdiff_plan* plan);
 
 /* ---- single kernels (unit tests call these; the plan calls the same launchers) ------------- */
 
-/* fp32 NCHW [n,3,H,W] x2 -> buffer 0 in `layout` (SEMDIFF_INPUT_*), GT images first */
-int semdiff_pack_input(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
-                       int32_t precision, int32_t layout, semdiff_stream_t stream);
+/* NCHW [n,3,H,W] x2 (element type in_precision) -> buffer 0 in `layout` (SEMDIFF_INPUT_*), GT images first */
+int semdiff_pack_input(const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H, int32_t W,
+                       void* out, int32_t precision, int32_t layout, semdiff_stream_t stream);
 
 /* out = act(conv(in, weight[:, :kh*kw*cin]) (+ conv1x1_stride2(in2, weight[:, kh*kw*cin:])) + bias (+ residual));
  * NHWC; in2 may be NULL; impl = SEMDIFF_CONV_* */

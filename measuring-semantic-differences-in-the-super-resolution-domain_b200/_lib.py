@@ -32,11 +32,11 @@ SIGNATURES = {
     "semdiff_plan_destroy": (_I, [_P]),
     "semdiff_plan_set_conv_impl": (_I, [_P, _I]),
     "semdiff_workspace_bytes": (_L, [_P, _I, _I, _I]),
-    "semdiff_score": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
+    "semdiff_score": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
     "semdiff_plan_set_profiling": (_I, [_P, _I]),
     "semdiff_plan_get_profile": (_I, [_P, C.POINTER(C.c_float), C.POINTER(_I), _I, _I]),
     "semdiff_plan_last_launches": (_L, [_P]),
-    "semdiff_pack_input": (_I, [_P, _P, _I, _I, _I, _P, _I, _I, _P]),
+    "semdiff_pack_input": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
     "semdiff_conv2d": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "semdiff_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),

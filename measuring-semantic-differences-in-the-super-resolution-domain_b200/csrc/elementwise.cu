@@ -7,17 +7,29 @@
 
 namespace semdiff {
 
+// two consecutive image elements (fp32 / bf16 / fp16 input planes) as floats
+template <typename TIn> __device__ __forceinline__ void load2(const TIn* p, float& a, float& b) {
+  if constexpr (sizeof(TIn) == 4) {
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    a = v.x; b = v.y;
+  } else {
+    const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const TIn* h = reinterpret_cast<const TIn*>(&u);
+    a = Elem<TIn>::to_f(h[0]); b = Elem<TIn>::to_f(h[1]);
+  }
+}
+
 // fp32 NCHW [n,3,H,W] (gt, sr) -> NHWC [2n,H,W,8], channels 3..7 = 0.  One thread per pixel: the three
 // plane reads are coalesced across the warp, the write is one 16 B (32 B for fp32) vector per thread.
-template <typename T>
-__global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ gt, const float* __restrict__ sr,
+template <typename T, typename TIn>
+__global__ void __launch_bounds__(256) pack_kernel(const TIn* __restrict__ gt, const TIn* __restrict__ sr,
                                                    int n_pairs, int img0, int n_imgs, int hw, T* __restrict__ out) {
   const int64_t total = (int64_t)n_imgs * hw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int img = img0 + (int)(i / hw);
     const int pix = (int)(i % hw);
-    const float* src = (img < n_pairs ? gt + (int64_t)img * 3 * hw : sr + (int64_t)(img - n_pairs) * 3 * hw) + pix;
-    float f[8] = {__ldg(src), __ldg(src + hw), __ldg(src + 2 * hw), 0.f, 0.f, 0.f, 0.f, 0.f};
+    const TIn* src = (img < n_pairs ? gt + (int64_t)img * 3 * hw : sr + (int64_t)(img - n_pairs) * 3 * hw) + pix;
+    float f[8] = {Elem<TIn>::to_f(src[0]), Elem<TIn>::to_f(src[hw]), Elem<TIn>::to_f(src[2 * hw]), 0.f, 0.f, 0.f, 0.f, 0.f};
     if constexpr (sizeof(T) == 2) {
       *reinterpret_cast<uint4*>(out + i * 8) = pack8<T>(f);
     } else {
@@ -36,15 +48,15 @@ __global__ void __launch_bounds__(256) pack_kernel(const float* __restrict__ gt,
 // 49 x 8 a channel-padded 7x7 window would need.  One thread per (img, i, q, j): 6 float2 reads, 32 bytes written.
 // The same kernel serves SEMDIFF_INPUT_S2D_ROW2 (3x3 stride-2 pad-1 stems, CLIP): window of 2 s2d pixels starting one
 // to the left, one padding row on top (i -> y = 2*(i-1)+dy), slots j = 2, 3 zero (so the row is still 64 wide).
-template <typename T>
-__global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__ gt, const float* __restrict__ sr,
+template <typename T, typename TIn>
+__global__ void __launch_bounds__(256) pack_s2d_kernel(const TIn* __restrict__ gt, const TIn* __restrict__ sr,
                                                        int n_pairs, int img0, int H, int W, T* __restrict__ out,
                                                        int j_real, int off) {
   const int H2 = H / 2 + (j_real == 4 ? 3 : 1), W2 = W / 2;
   const int per_img = H2 * W2 * 4;
   const int img = img0 + blockIdx.y;
   const int plane = H * W;
-  const float* src = img < n_pairs ? gt + (int64_t)img * 3 * plane : sr + (int64_t)(img - n_pairs) * 3 * plane;
+  const TIn* src = img < n_pairs ? gt + (int64_t)img * 3 * plane : sr + (int64_t)(img - n_pairs) * 3 * plane;
   T* out_img = out + (int64_t)blockIdx.y * per_img * 16;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += gridDim.x * blockDim.x) {
     const int j = t & 3;
@@ -61,9 +73,7 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const float* __restrict__
         if (y < 0 || y >= H) continue;
 #pragma unroll
         for (int ci = 0; ci < 3; ++ci) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(src + ci * plane + y * W + x0));
-          f[(dy * 2 + 0) * 3 + ci] = v.x;
-          f[(dy * 2 + 1) * 3 + ci] = v.y;
+          load2<TIn>(src + ci * plane + y * W + x0, f[(dy * 2 + 0) * 3 + ci], f[(dy * 2 + 1) * 3 + ci]);
         }
       }
     }
@@ -199,22 +209,35 @@ static int grid_for(int64_t total, int block) {
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-template <typename T>
-static int pack_t(const float* gt, const float* sr, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
+template <typename T, typename TIn>
+static int pack_t(const void* gt_, const void* sr_, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
                   int layout, cudaStream_t st) {
+  const TIn* gt = (const TIn*)gt_;
+  const TIn* sr = (const TIn*)sr_;
   if (layout == SEMDIFF_INPUT_S2D_ROW4 || layout == SEMDIFF_INPUT_S2D_ROW2) {
     const bool row4 = layout == SEMDIFF_INPUT_S2D_ROW4;
     const int per_img = (H / 2 + (row4 ? 3 : 1)) * (W / 2) * 4;
     dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)n_imgs);
-    pack_s2d_kernel<T><<<grid, 256, 0, st>>>(gt, sr, n_pairs, img0, H, W, (T*)out, row4 ? 4 : 2, row4 ? 2 : 1);
+    pack_s2d_kernel<T, TIn><<<grid, 256, 0, st>>>(gt, sr, n_pairs, img0, H, W, (T*)out, row4 ? 4 : 2, row4 ? 2 : 1);
   } else {
     const int64_t total = (int64_t)n_imgs * H * W;
-    pack_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, img0, n_imgs, H * W, (T*)out);
+    pack_kernel<T, TIn><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, img0, n_imgs, H * W, (T*)out);
   }
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
-int launch_pack(const float* gt, const float* sr, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
+template <typename T>
+static int pack_in(const void* gt, const void* sr, int n_pairs, int img0, int n_imgs, int H, int W, void* out, int layout,
+                   int in_precision, cudaStream_t st) {
+  switch (in_precision) {
+    case SEMDIFF_FP32: return pack_t<T, float>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+    case SEMDIFF_BF16: return pack_t<T, __nv_bfloat16>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+    case SEMDIFF_FP16: return pack_t<T, __half>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+  }
+  set_error("pack: bad input precision %d", in_precision);
+  return SEMDIFF_ERR_ARG;
+}
+int launch_pack(const void* gt, const void* sr, int in_precision, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
                 int precision, int layout, cudaStream_t st) {
   if (n_pairs <= 0 || H <= 0 || W <= 0 || img0 < 0 || n_imgs <= 0 || img0 + n_imgs > 2 * n_pairs) {
     set_error("pack: bad shape");
@@ -223,9 +246,9 @@ int launch_pack(const float* gt, const float* sr, int n_pairs, int img0, int n_i
   if (layout != SEMDIFF_INPUT_NHWC8 && ((H | W) & 1)) { set_error("pack: the s2d stem layouts need even H and W"); return SEMDIFF_ERR_ARG; }
   if (layout < SEMDIFF_INPUT_NHWC8 || layout > SEMDIFF_INPUT_S2D_ROW2) { set_error("pack: bad layout %d", layout); return SEMDIFF_ERR_ARG; }
   switch (precision) {
-    case SEMDIFF_BF16: return pack_t<__nv_bfloat16>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
-    case SEMDIFF_FP16: return pack_t<__half>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
-    case SEMDIFF_FP32: return pack_t<float>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+    case SEMDIFF_BF16: return pack_in<__nv_bfloat16>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, in_precision, st);
+    case SEMDIFF_FP16: return pack_in<__half>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, in_precision, st);
+    case SEMDIFF_FP32: return pack_in<float>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, in_precision, st);
   }
   set_error("pack: bad precision %d", precision);
   return SEMDIFF_ERR_ARG;

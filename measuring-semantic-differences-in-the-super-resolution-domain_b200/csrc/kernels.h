@@ -27,8 +27,9 @@ inline size_t elem_bytes(int precision) { return precision == SEMDIFF_FP32 ? 4 :
 
 // each returns 0 / negative error code; all asynchronous on `stream`
 // images [img0, img0 + n_imgs) of the stacked (GT..., SR...) batch -> out[0 .. n_imgs)
-int launch_pack(const float* gt, const float* sr, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
-                int precision, int layout, cudaStream_t stream);
+// gt / sr element type = in_precision (SEMDIFF_FP32 / BF16 / FP16), NCHW planes
+int launch_pack(const void* gt, const void* sr, int in_precision, int n_pairs, int img0, int n_imgs, int H, int W,
+                void* out, int precision, int layout, cudaStream_t stream);
 int launch_maxpool3x3s2(const void* in, void* out, int n_img, int H, int W, int c, int precision, cudaStream_t stream);
 int launch_avgpool(const void* in, void* out, int n_img, int H, int W, int c, int window, int precision,
                    cudaStream_t stream);

@@ -323,14 +323,15 @@ int semdiff_plan_get_profile(semdiff_plan* P, float* out_ms, int32_t* out_launch
 
 int64_t semdiff_plan_last_launches(const semdiff_plan* P) { return P ? P->last_launches : -1; }
 
-int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W,
-                  int32_t mb, const float* head_w, const float* head_b, int32_t normalize, void* workspace,
+int semdiff_score(semdiff_plan* P, const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H,
+                  int32_t W, int32_t mb, const float* head_w, const float* head_b, int32_t normalize, void* workspace,
                   int64_t workspace_bytes, float* out_scores, float* out_pre_relu, float* out_chan_mean,
                   semdiff_stream_t stream_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
   if (P == nullptr || gt == nullptr || sr == nullptr || head_w == nullptr || head_b == nullptr || workspace == nullptr ||
       out_scores == nullptr) { set_error("score: null argument"); return SEMDIFF_ERR_ARG; }
   if (n_pairs < 0 || H <= 0 || W <= 0 || mb <= 0) { set_error("score: bad sizes"); return SEMDIFF_ERR_ARG; }
+  if (in_precision < SEMDIFF_BF16 || in_precision > SEMDIFF_FP32) { set_error("score: bad input precision %d", in_precision); return SEMDIFF_ERR_ARG; }
   P->last_launches = 0;
   if (n_pairs == 0) return 0;  // empty batch -> empty result, like the reference
   if (mb > n_pairs) mb = n_pairs;
@@ -356,8 +357,9 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
     float* partials = reinterpret_cast<float*>(ws + S.partial_offset);
     int tap_parts[16], tap_hw[16];
     const int n_img = 2 * cur;
-    const float* gt_mb = gt + p0 * img_elems;
-    const float* sr_mb = sr + p0 * img_elems;
+    const int64_t in_bytes = (int64_t)elem_bytes(in_precision);
+    const char* gt_mb = reinterpret_cast<const char*>(gt) + p0 * img_elems * in_bytes;
+    const char* sr_mb = reinterpret_cast<const char*>(sr) + p0 * img_elems * in_bytes;
     // one op on `imgs` images; dst_img0 offsets the destination (head chunks write into the full-batch buffer)
     auto run_op = [&](int i, int imgs, int dst_img0, bool tail_launch) -> int {
       const semdiff_op& op = P->ops[i];
@@ -401,7 +403,7 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
         const int cn = n_img - c0 < S.chunk_imgs ? n_img - c0 : S.chunk_imgs;
         {
           ProfScope ps(P, n_ops + 0, st);
-          int rc = launch_pack(gt_mb, sr_mb, cur, c0, cn, H, W, ws + S.buf_offset[0], P->precision, P->input_layout, st);
+          int rc = launch_pack(gt_mb, sr_mb, in_precision, cur, c0, cn, H, W, ws + S.buf_offset[0], P->precision, P->input_layout, st);
           if (rc != 0) return rc;
           P->last_launches++;
         }
@@ -413,7 +415,7 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
       first_op = P->head_ops;
     } else {
       ProfScope ps(P, n_ops + 0, st);
-      int rc = launch_pack(gt_mb, sr_mb, cur, 0, n_img, H, W, ws + S.buf_offset[0], P->precision, P->input_layout, st);
+      int rc = launch_pack(gt_mb, sr_mb, in_precision, cur, 0, n_img, H, W, ws + S.buf_offset[0], P->precision, P->input_layout, st);
       if (rc != 0) return rc;
       P->last_launches++;
     }
@@ -432,9 +434,10 @@ int semdiff_score(semdiff_plan* P, const float* gt, const float* sr, int32_t n_p
   return 0;
 }
 
-int semdiff_pack_input(const float* gt, const float* sr, int32_t n_pairs, int32_t H, int32_t W, void* out,
-                       int32_t precision, int32_t layout, semdiff_stream_t st) {
-  return launch_pack(gt, sr, n_pairs, 0, 2 * n_pairs, H, W, out, precision, layout, reinterpret_cast<cudaStream_t>(st));
+int semdiff_pack_input(const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H, int32_t W,
+                       void* out, int32_t precision, int32_t layout, semdiff_stream_t st) {
+  return launch_pack(gt, sr, in_precision, n_pairs, 0, 2 * n_pairs, H, W, out, precision, layout,
+                     reinterpret_cast<cudaStream_t>(st));
 }
 
 int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out, int32_t n_img,

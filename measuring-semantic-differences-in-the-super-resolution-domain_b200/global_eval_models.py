@@ -218,8 +218,10 @@ class _B200Scorer(nn.Module):
     def _run(self, a, b, head_w, head_b, want_grad: bool = False):
         n, _, H, W = a.shape
         plan = self.plan(H % 2 == 0 and W % 2 == 0)
-        a = a.detach().contiguous().float()
-        b = b.detach().contiguous().float()
+        in_dt = a.dtype if a.dtype in (torch.bfloat16, torch.float16) and b.dtype == a.dtype else torch.float32
+        a = a.detach().contiguous().to(in_dt)
+        b = b.detach().contiguous().to(in_dt)
+        in_prec = {torch.float32: _lib.FP32, torch.bfloat16: _lib.BF16, torch.float16: _lib.FP16}[in_dt]
         hw_, hb_ = head_w.detach().contiguous(), head_b.detach().contiguous()
         out = torch.empty(n, dtype=torch.float32, device=a.device)
         if n == 0:
@@ -229,7 +231,7 @@ class _B200Scorer(nn.Module):
         pre = torch.empty_like(out) if want_grad else None
         chan = torch.empty(n, hw_.numel(), dtype=torch.float32, device=a.device) if want_grad else None
         with torch.cuda.device(a.device):
-            rc = plan.lib.semdiff_score(plan.handle, a.data_ptr(), b.data_ptr(), n, H, W, mb, hw_.data_ptr(),
+            rc = plan.lib.semdiff_score(plan.handle, a.data_ptr(), b.data_ptr(), in_prec, n, H, W, mb, hw_.data_ptr(),
                                         hb_.data_ptr(), int(self.normalize), ws.data_ptr(), ws.numel(),
                                         out.data_ptr(), pre.data_ptr() if want_grad else None,
                                         chan.data_ptr() if want_grad else None, _lib.stream_ptr())
@@ -240,7 +242,8 @@ class _B200Scorer(nn.Module):
     @torch.no_grad()
     def score_host(self, gt_host: torch.Tensor, sr_host: torch.Tensor, out_host: torch.Tensor | None = None,
                    chunk_pairs: int | None = None, wait: bool = True):
-        """End-to-end scoring of HOST tensors (pinned fp32 [N,3,H,W]) -> host scores [N].
+        """End-to-end scoring of HOST tensors (pinned [N,3,H,W]; fp32 as the reference's datasets produce them, or
+        bf16/fp16, which halves the PCIe bytes) -> host scores [N].
 
         The images cross PCIe on a copy stream into a ring of two device staging slots while the previous slot is
         being scored on the current stream, so the transfer overlaps the kernels - within one call when it spans
@@ -259,12 +262,13 @@ class _B200Scorer(nn.Module):
         head_w = torch.cat([m.weight.reshape(-1) for m in self.w_layers]).float()
         head_b = torch.cat([m.bias.reshape(-1) for m in self.w_layers]).float()
         chunk = min(chunk_pairs or self.default_microbatch(H, W), n)
-        if getattr(self, "_stage_shape", None) != (chunk, H, W):
+        if getattr(self, "_stage_shape", None) != (chunk, H, W, gt_host.dtype):
             torch.cuda.synchronize(dev)
-            self._stage = [(torch.empty(chunk, 3, H, W, device=dev), torch.empty(chunk, 3, H, W, device=dev)) for _ in range(2)]
+            self._stage = [(torch.empty(chunk, 3, H, W, device=dev, dtype=gt_host.dtype),
+                            torch.empty(chunk, 3, H, W, device=dev, dtype=gt_host.dtype)) for _ in range(2)]
             self._stage_consumed = [None, None]       # event: the scoring that last read this slot has finished
             self._stage_next = 0
-            self._stage_shape = (chunk, H, W)
+            self._stage_shape = (chunk, H, W, gt_host.dtype)
             self._copy_stream = torch.cuda.Stream(device=dev)
         out_dev = torch.empty(n, dtype=torch.float32, device=dev)
         for lo in range(0, n, chunk):

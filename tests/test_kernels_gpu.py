@@ -18,7 +18,7 @@ def test_pack(precision):
     gt = torch.randn(3, 3, 20, 28, device=DEV, generator=g)
     sr = torch.randn(3, 3, 20, 28, device=DEV, generator=g)
     out = torch.full((6, 20, 28, 8), 7.0, dtype=DT[precision], device=DEV)
-    _lib.check(lib().semdiff_pack_input(gt.data_ptr(), sr.data_ptr(), 3, 20, 28, out.data_ptr(), _lib.PRECISIONS[precision],
+    _lib.check(lib().semdiff_pack_input(gt.data_ptr(), sr.data_ptr(), _lib.FP32, 3, 20, 28, out.data_ptr(), _lib.PRECISIONS[precision],
                                         _lib.INPUT_NHWC8, sp()), "pack")
     ref = torch.cat([gt, sr]).permute(0, 2, 3, 1).to(DT[precision])
     assert torch.equal(out[..., :3], ref)
@@ -32,7 +32,7 @@ def test_pack_s2d_row_window(precision):
     gt = torch.randn(2, 3, H, W, device=DEV, generator=g)
     sr = torch.randn(2, 3, H, W, device=DEV, generator=g)
     out = torch.full((4, H // 2 + 3, W // 2, 64), 7.0, dtype=DT[precision], device=DEV)
-    _lib.check(lib().semdiff_pack_input(gt.data_ptr(), sr.data_ptr(), 2, H, W, out.data_ptr(), _lib.PRECISIONS[precision],
+    _lib.check(lib().semdiff_pack_input(gt.data_ptr(), sr.data_ptr(), _lib.FP32, 2, H, W, out.data_ptr(), _lib.PRECISIONS[precision],
                                         _lib.INPUT_S2D_ROW4, sp()), "pack")
     x = torch.cat([gt, sr])
     ref = torch.zeros(4, H // 2 + 3, W // 2, 64, device=DEV)
@@ -46,6 +46,21 @@ def test_pack_s2d_row_window(precision):
                             c = j * 16 + (dy * 2 + dx) * 3
                             ref[:, i, q, c:c + 3] = x[:, :, y, xx]
     assert torch.equal(out, ref.to(DT[precision]))
+
+
+@pytest.mark.parametrize("layout", [_lib.INPUT_NHWC8, _lib.INPUT_S2D_ROW4, _lib.INPUT_S2D_ROW2])
+def test_pack_16bit_inputs_equal_fp32_inputs_of_the_same_values(layout):
+    """bf16 host images packed directly == the same values passed as fp32 (the pack kernel rounds to bf16 anyway)."""
+    H, W = 16, 24
+    gt = torch.randn(2, 3, H, W, device=DEV).bfloat16()
+    sr = torch.randn(2, 3, H, W, device=DEV).bfloat16()
+    shape = {0: (4, H, W, 8), 1: (4, H // 2 + 3, W // 2, 64), 2: (4, H // 2 + 1, W // 2, 64)}[layout]
+    a = torch.full(shape, 3.0, dtype=torch.bfloat16, device=DEV)
+    b = torch.full(shape, 5.0, dtype=torch.bfloat16, device=DEV)
+    _lib.check(lib().semdiff_pack_input(gt.data_ptr(), sr.data_ptr(), _lib.BF16, 2, H, W, a.data_ptr(), _lib.BF16, layout, sp()), "pack")
+    g32, s32 = gt.float(), sr.float()
+    _lib.check(lib().semdiff_pack_input(g32.data_ptr(), s32.data_ptr(), _lib.FP32, 2, H, W, b.data_ptr(), _lib.BF16, layout, sp()), "pack")
+    assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
