@@ -32,10 +32,16 @@ constexpr int BLOCK_K = 64;  // 64 x 16-bit = one 128-byte swizzle row
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 enum { A_TMA = 0, A_GATHER = 1, A_IM2COL = 2 };
 
-template <int BLOCK_N> struct TcCfg {
+// kBRes ("B resident"): the whole weight matrix of the conv (one n-tile, <= MAX_RES_KB k-blocks) is loaded into shared
+// memory ONCE per CTA and the ring only cycles activation tiles - for the 64-output-channel convs (stems, layer1 3x3s)
+// whose tiles are bound by L2->SM operand traffic, this removes a third of it and doubles the ring depth.
+constexpr int MAX_RES_KB = 9;  // 9 x 64 = 576 = 3x3x64
+
+template <int BLOCK_N, bool kBRes = false> struct TcCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES = BLOCK_N >= 128 ? 4 : 6;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + (kBRes ? 0 : B_STAGE_BYTES);
+  static constexpr int STAGES = kBRes ? 6 : (BLOCK_N >= 128 ? 4 : 6);
+  static constexpr int B_REGION_BYTES = kBRes ? MAX_RES_KB * B_STAGE_BYTES : STAGES * B_STAGE_BYTES;
   static constexpr int GATHER_LAG = STAGES - 2;        // cp.async groups in flight per gather thread
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   // epilogue staging: the tile is written out in column groups, each group = BOXES TMA boxes of BOX_COLS columns
@@ -46,8 +52,9 @@ template <int BLOCK_N> struct TcCfg {
   static constexpr int BOX_BYTES = BLOCK_M * BOX_COLS * 2;
   static constexpr int GROUP_BYTES = BOXES * BOX_BYTES;
   static constexpr int RING = BLOCK_N == 256 ? 1 : 3;   // BLOCK_N == 256 never carries a residual
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RING;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING * GROUP_BYTES + NUM_BARS * 8 + 16 + 1024;
+  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RING + 1;
+  static constexpr int SMEM_BYTES = STAGES * A_STAGE_BYTES + B_REGION_BYTES + RING * GROUP_BYTES + NUM_BARS * 8 + 16 + 1024;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
 struct alignas(64) ConvTcParams {
@@ -76,23 +83,24 @@ template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int cta_threads
   return kAMode == A_GATHER ? 352 : (2 + epi_warps<BLOCK_N, kAMode>() + 1) * 32;
 }
 
-template <typename T, int BLOCK_N, int kAMode>
+template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
 __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, kBRes>;
   constexpr int EPI_WARPS = epi_warps<BLOCK_N, kAMode>();
   constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* smem_c = smem + STAGES * Cfg::STAGE_BYTES;
+  uint8_t* smem_c = smem_b + Cfg::B_REGION_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + RING * Cfg::GROUP_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* res_full_bar = tmem_empty_bar + 2;
   uint64_t* c_free_bar = res_full_bar + RING;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(c_free_bar + RING);
+  uint64_t* bres_bar = c_free_bar + RING;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -118,6 +126,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
       mbar_init(&res_full_bar[i], 1);
       mbar_init(&c_free_bar[i], 1);
     }
+    mbar_init(bres_bar, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
@@ -131,6 +140,11 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     if (leader) {
       int stage = 0, phase = 0;
       const int kb_per_tap = p.Cin >> 6;
+      if (kBRes) {  // the whole weight matrix, once
+        mbar_arrive_expect_tx(bres_bar, p.num_kb * Cfg::B_STAGE_BYTES);
+        for (int kb = 0; kb < p.num_kb; ++kb)
+          tma_load_2d(&p.tmB, bres_bar, smem_b + kb * Cfg::B_STAGE_BYTES, kb * BLOCK_K, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int n = 0, h0 = 0, w0 = 0, h2 = 0, w2 = 0;
@@ -147,7 +161,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
         int tap = 0, cb = 0;  // filter tap and 64-channel block of the current k-block (im2col)
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], Cfg::B_STAGE_BYTES + (kAMode != A_GATHER ? A_STAGE_BYTES : 0));
+          mbar_arrive_expect_tx(&full_bar[stage], (kBRes ? 0 : Cfg::B_STAGE_BYTES) + (kAMode != A_GATHER ? A_STAGE_BYTES : 0));
           if (kb >= p.num_kb1) {
             const int kb2 = kb - p.num_kb1;  // fused 1x1 conv over the second activation tensor
             if (p.a2_im2col)
@@ -162,7 +176,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
                                (uint16_t)s, (uint16_t)r);
             if (++cb == kb_per_tap) { cb = 0; ++tap; }
           }
-          tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BLOCK_N);
+          if (!kBRes)
+            tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -174,6 +189,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(smem_a));
     const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(smem_b));
     int stage = 0, phase = 0, local = 0;
+    if (kBRes && blockIdx.x < total_tiles) mbar_wait(bres_bar, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -184,7 +200,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
         tcgen05_fence_after();
         if (leader) {
           const uint64_t a_desc = a_desc0 + (uint64_t)((stage * A_STAGE_BYTES) >> 4);
-          const uint64_t b_desc = b_desc0 + (uint64_t)((stage * Cfg::B_STAGE_BYTES) >> 4);
+          const uint64_t b_desc = b_desc0 + (uint64_t)(((kBRes ? kb : stage) * Cfg::B_STAGE_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
             umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -479,11 +495,11 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <typename T, int BLOCK_N, int kAMode>
+template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
 static int launch_t(const ConvTcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N>;
+  using Cfg = TcCfg<BLOCK_N, kBRes>;
   static bool configured = false;
-  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode>;
+  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode, kBRes>;
   if (!configured) {
     SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured = true;
@@ -500,7 +516,11 @@ static int launch_n(const ConvTcParams& p, int block_n, cudaStream_t st) {
   switch (block_n) {
     case 256: return launch_t<T, 256, kAMode>(p, st);
     case 128: return launch_t<T, 128, kAMode>(p, st);
-    case 64: return launch_t<T, 64, kAMode>(p, st);
+    case 64:
+      if constexpr (kAMode != A_GATHER) {
+        if (p.n_tiles == 1 && p.num_kb <= MAX_RES_KB) return launch_t<T, 64, kAMode, true>(p, st);
+      }
+      return launch_t<T, 64, kAMode>(p, st);
     case 32: return launch_t<T, 32, kAMode>(p, st);
   }
   set_error("conv_tc: unsupported BLOCK_N %d", block_n);
