@@ -232,3 +232,47 @@ def test_wperlay_variant(depth):
         with torch.no_grad():
             got = model(gt.cuda(), sr.cuda()).cpu()
         assert rel_err(got, ref) < tol, (precision, got, ref)
+
+
+def test_high_resolution_pair_1024():
+    """BASELINE.json configs[4] geometry: 1024x1024 pairs (taps 256^2 .. 32^2); bf16 tensor-core path vs the fp32 path."""
+    _, m32 = oracle_and_module("resnet50", 3, "fp32")
+    _, m16 = oracle_and_module("resnet50", 3, "bf16")
+    g = torch.Generator().manual_seed(8)
+    gt = torch.randn(1, 3, 1024, 1024, generator=g)
+    sr = (gt + 0.3 * torch.randn(1, 3, 1024, 1024, generator=g)) / (1 + 0.09) ** 0.5
+    with torch.no_grad():
+        s32 = m32(gt.cuda(), sr.cuda()).cpu()
+        s16 = m16(gt.cuda(), sr.cuda()).cpu()
+    assert m16.default_microbatch(1024, 1024) == 12
+    assert torch.isfinite(s32).all() and rel_err(s16, s32) < 6e-2, (s16, s32)
+
+
+def test_c_abi_error_paths():
+    """Every failure is a negative return code + message, never a crash or a silent fallback."""
+    import ctypes as C
+    from semdiff_b200 import _lib
+    oracle, model = oracle_and_module("resnet50", 0, "bf16")
+    plan = model.plan()
+    lib = plan.lib
+    gt, sr = make_pairs(1, seed=1)
+    gt, sr = gt.cuda(), sr.cuda()
+    hw = torch.ones(2048, device="cuda"); hb = torch.zeros(1, device="cuda"); out = torch.empty(1, device="cuda")
+    small = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    rc = lib.semdiff_score(plan.handle, gt.data_ptr(), sr.data_ptr(), _lib.FP32, 1, 224, 224, 1, hw.data_ptr(), hb.data_ptr(), 0,
+                           small.data_ptr(), small.numel(), out.data_ptr(), None, None, _lib.stream_ptr())
+    assert rc == -1 and b"workspace too small" in lib.semdiff_last_error()
+    rc = lib.semdiff_score(plan.handle, None, sr.data_ptr(), _lib.FP32, 1, 224, 224, 1, hw.data_ptr(), hb.data_ptr(), 0,
+                           small.data_ptr(), small.numel(), out.data_ptr(), None, None, _lib.stream_ptr())
+    assert rc == -1 and b"null argument" in lib.semdiff_last_error()
+    assert lib.semdiff_workspace_bytes(plan.handle, 1, 225, 224) < 0          # s2d stem layout needs even sizes
+    x = torch.zeros(1, 8, 8, 24, dtype=torch.bfloat16, device="cuda")           # cin 24 is not a tensor-core shape
+    w = torch.zeros(64, 24, dtype=torch.bfloat16, device="cuda"); b = torch.zeros(64, device="cuda")
+    o = torch.empty(1, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
+    rc = lib.semdiff_conv2d(x.data_ptr(), w.data_ptr(), b.data_ptr(), None, o.data_ptr(), 1, 8, 8, 24, 64, 1, 1, 1, 0, 1,
+                            None, 0, 0, 0, 1, _lib.BF16, _lib.CONV_TC_TMA, _lib.stream_ptr())
+    assert rc == -3 and b"unsupported shape" in lib.semdiff_last_error()
+    with pytest.raises(ValueError):
+        model(gt, sr[:, :, :100])
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        model(gt.cpu(), sr.cpu())
