@@ -142,6 +142,23 @@ int semdiff_head(const float* partials, int32_t n_taps, int32_t n_pairs, const i
                  const int32_t* hw, const float* head_b, float* out_scores, float* out_pre_relu,
                  semdiff_stream_t stream);
 
+/* ---- on-device preprocessing: the reference's `model.processor` (timm eval transform on PIL images, :333-334) ----
+ * Pillow's 8-bit bicubic resize (separable, antialiased, Q22 fixed point, uint8 after each pass) -> center crop ->
+ * /255 -> (x - mean) / std -> NCHW, bit-exact against Pillow + torchvision.
+ * semdiff_resize_ksize / semdiff_resize_coeffs are HOST functions: bounds [out_size][2] = (first tap, taps),
+ * coeffs [out_size][ksize] Q22.  The caller uploads the tables and passes device pointers to semdiff_preprocess_u8:
+ *   src   device uint8 [n, Hs, Ws, 3] (decoded RGB, HWC);  the image is (virtually) resized to Hr x Wr and the window
+ *         [top, top+crop_h) x [left, left+crop_w) is produced;  tmp: device uint8 [n, Hs, crop_w, 3] scratch
+ *   out   device [n, 3, crop_h, crop_w] in out_precision (SEMDIFF_FP32 = what the reference's processor returns)
+ *   mean, stdv: HOST float[3] */
+int32_t semdiff_resize_ksize(int32_t in_size, int32_t out_size);
+int semdiff_resize_coeffs(int32_t in_size, int32_t out_size, int32_t* bounds, int32_t* coeffs);
+int semdiff_preprocess_u8(const uint8_t* src, int32_t n, int32_t Hs, int32_t Ws, int32_t Hr, int32_t Wr, int32_t top,
+                          int32_t left, int32_t crop_h, int32_t crop_w, const int32_t* bounds_x, const int32_t* coeffs_x,
+                          int32_t ksize_x, const int32_t* bounds_y, const int32_t* coeffs_y, int32_t ksize_y,
+                          const float* mean, const float* stdv, uint8_t* tmp, void* out, int32_t out_precision,
+                          semdiff_stream_t stream);
+
 const char* semdiff_last_error(void);
 /* "semdiff_b200 <version> sm_100a" */
 const char* semdiff_version(void);

@@ -43,6 +43,10 @@ SIGNATURES = {
     "semdiff_distance_parts": (_I, [_I, _I]),
     "semdiff_layer_distance": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _I, _I, _P]),
     "semdiff_head": (_I, [_P, _I, _I, C.POINTER(_I), C.POINTER(_I), _P, _P, _P, _P]),
+    "semdiff_resize_ksize": (_I, [_I, _I]),
+    "semdiff_resize_coeffs": (_I, [_I, _I, _P, _P]),
+    "semdiff_preprocess_u8": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, C.POINTER(C.c_float),
+                                   C.POINTER(C.c_float), _P, _P, _I, _P]),
     "semdiff_last_error": (C.c_char_p, []),
     "semdiff_version": (C.c_char_p, []),
 }

@@ -26,6 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib, trunks
+from .preprocess import GpuProcessor
 from .processor import make_processor
 
 
@@ -143,7 +144,8 @@ class _B200Scorer(nn.Module):
         self.wanted_layers = self._tap_names(depth)
         print(self.wanted_layers)  # the reference prints this too (:328 / :702)
         cfg = getattr(self.clip, "pretrained_cfg", None) or {}
-        self.processor = make_processor(dict(cfg))
+        self.processor = make_processor(dict(cfg))          # CPU, per PIL image: what the reference's datasets call
+        self.gpu_processor = GpuProcessor(dict(cfg), dev)   # the same transform for uint8 batches on the device
         self.w_layers = nn.ModuleList([nn.Conv2d(c, 1, kernel_size=1, stride=1) for c in self._tap_channels(depth)])
         self.final_relu = nn.ReLU()
         self.w_layers.to(dev)
@@ -238,6 +240,13 @@ class _B200Scorer(nn.Module):
         _lib.check(rc, "semdiff_score")
         return out, pre, chan
 
+
+    @torch.no_grad()
+    def score_uint8(self, a_u8: torch.Tensor, b_u8: torch.Tensor) -> torch.Tensor:
+        """forward() on decoded uint8 [N, H, W, 3] CUDA batches: `processor` runs on the device (bit-exact Pillow
+        bicubic + crop + normalise), then the scorer; in the 16-bit modes the images go straight to the trunk's type."""
+        dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[self.precision]
+        return self(self.gpu_processor(a_u8, dt), self.gpu_processor(b_u8, dt))
 
     @torch.no_grad()
     def score_host(self, gt_host: torch.Tensor, sr_host: torch.Tensor, out_host: torch.Tensor | None = None,

@@ -276,3 +276,37 @@ def test_c_abi_error_paths():
         model(gt, sr[:, :, :100])
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         model(gt.cpu(), sr.cpu())
+
+
+def test_reference_training_loop_runs_and_tracks_the_oracle():
+    """The caller in /root/reference/CLIPLPIPS_REG_training_sweep_example.py:48-100 (Adam over model.parameters(), MSE
+    loss, model.train()/eval()) must work unchanged: a few steps here follow the same loss trajectory as the oracle
+    trained with torch autograd (frozen eval-mode trunk)."""
+    oracle, model = oracle_and_module("resnet50", 2, "fp32")
+    import copy
+    ref = RestatedScorer("resnet50", 2, seed=0)
+    ref.load_state_dict(oracle.state_dict())
+    gt, sr = make_pairs(4, seed=23)
+    target = torch.tensor([0.2, 0.9, 0.4, 0.6]) * 40
+    opt = torch.optim.Adam(model.parameters(), lr=1e-2)
+    opt_ref = torch.optim.Adam(ref.w_layers.parameters(), lr=1e-2)
+    fa, fb = ref.features(gt), ref.features(sr)
+    d2 = [((a - b) ** 2).detach() for a, b in zip(fa, fb)]
+    losses, losses_ref = [], []
+    for _ in range(4):
+        model.train()
+        opt.zero_grad()
+        loss = torch.nn.functional.mse_loss(model(sr.cuda(), gt.cuda()), target.cuda())
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+        opt_ref.zero_grad()
+        out = torch.relu(torch.stack([ref.w_layers[j](d).squeeze(1).mean((-1, -2)) for j, d in enumerate(d2)]).mean(0))
+        lr_ = torch.nn.functional.mse_loss(out, target)
+        lr_.backward()
+        opt_ref.step()
+        losses_ref.append(lr_.item())
+    print(f"[train] losses {losses} oracle {losses_ref}")
+    assert losses[-1] < losses[0]
+    assert all(abs(a - b) <= 1e-3 * abs(b) + 1e-6 for a, b in zip(losses, losses_ref))
+    assert not model.clip.training and all(p.grad is None for p in model.clip.parameters())
