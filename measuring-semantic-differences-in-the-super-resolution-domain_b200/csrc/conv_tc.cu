@@ -484,25 +484,32 @@ bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma) {
   return s.M() > 0 && s.M() < (int64_t)1 << 31;
 }
 
-static int g_num_sms = 0;
+// per-device caches (a process may drive several GPUs; function attributes and SM counts are per device)
+constexpr int MAX_DEVICES = 64;
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < MAX_DEVICES ? dev : 0;
+}
 static int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (g_num_sms <= 0) g_num_sms = 148;
+  static int sms[MAX_DEVICES] = {};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (sms[dev] <= 0) sms[dev] = 148;
   }
-  return g_num_sms;
+  return sms[dev];
 }
 
 template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
 static int launch_t(const ConvTcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, kBRes>;
-  static bool configured = false;
+  static bool configured[MAX_DEVICES] = {};
   auto kern = conv_tc_kernel<T, BLOCK_N, kAMode, kBRes>;
-  if (!configured) {
+  const int dev = current_device();
+  if (!configured[dev]) {
     SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
