@@ -33,7 +33,8 @@ template <> struct Elem<__nv_bfloat16> {
 };
 template <> struct Elem<__half> {
   static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
-  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+  // saturating: an activation beyond the fp16 range becomes +-65504, never inf (which would turn a-b into NaN)
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f)); }
   static constexpr uint32_t kUmmaFormat = 0;  // F16F32Format::F16
 };
 template <> struct Elem<float> {
