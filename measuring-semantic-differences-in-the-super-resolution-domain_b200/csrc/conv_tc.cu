@@ -21,7 +21,6 @@
 // Pipelines: smem ring full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue),
 //            C ring res_full/c_free (residual loader <-> epilogue/TMA store).
 #include <cuda.h>
-#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -69,7 +68,6 @@ struct alignas(64) ConvTcParams {
   int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, relu, has_res;
   int M, num_kb, m_tiles, n_tiles, cpt, taps;
   int num_kb1, a2_im2col, stride2;  // k-blocks [num_kb1, num_kb) come from the second source
-  int multicast;                    // launched as clusters of 2 CTAs sharing the activation tile (kMC)
 };
 static_assert(sizeof(ConvTcParams) <= 896, "ConvTcLaunch::params too small");
 
@@ -85,10 +83,7 @@ template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int cta_threads
   return kAMode == A_GATHER ? 352 : (2 + epi_warps<BLOCK_N, kAMode>() + 1) * 32;
 }
 
-// kMC ("multicast pair"): a cluster of 2 CTAs computes ONE 128-row tile of a conv with Cout = 2 * BLOCK_N; each CTA
-// owns half of the output channels and TMA-loads half of the activation rows, multicast to both.  The narrow convs
-// (Cout 64 / 128: stems, 3x3 of the first two stages) are bound by L2 -> SM operand traffic, which this halves.
-template <typename T, int BLOCK_N, int kAMode, bool kBRes = false, bool kMC = false>
+template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
 __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = TcCfg<BLOCK_N, kBRes>;
   constexpr int EPI_WARPS = epi_warps<BLOCK_N, kAMode>();
@@ -108,13 +103,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // tile schedule: (m_tile, n_tile) pairs round-robin over CTAs; multicast pairs walk the m-tiles together and the
-  // cluster rank is the n-tile
-  const int cta_rank = kMC ? (int)cluster_ctarank() : 0;
-  const int t_first = kMC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int t_step = kMC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int t_limit = kMC ? p.m_tiles : p.m_tiles * p.n_tiles;
-  constexpr int A_ROWS = kMC ? BLOCK_M / 2 : BLOCK_M;  // activation rows this CTA loads itself
+  const int total_tiles = p.m_tiles * p.n_tiles;
   // one lane per warp, elected once: ptxas then knows that the single-thread roles below (TMA / tcgen05 issue) are
   // single-lane and emits the uniform-datapath instructions directly instead of an elect-and-retry loop per instruction
   const bool leader = elect_one();
@@ -127,7 +116,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     if (p.has_res) tma_prefetch_desc(&p.tmR);
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full_bar[i], kAMode == A_GATHER ? 1 + 4 : 1);
-      mbar_init(&empty_bar[i], kMC ? 2 : 1);
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
@@ -143,7 +132,6 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
   if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   tcgen05_fence_before();
   __syncthreads();
-  if (kMC) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast to them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -155,13 +143,13 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
       if (kBRes) {  // the whole weight matrix, once
         mbar_arrive_expect_tx(bres_bar, p.num_kb * Cfg::B_STAGE_BYTES);
         for (int kb = 0; kb < p.num_kb; ++kb)
-          tma_load_2d(&p.tmB, bres_bar, smem_b + kb * Cfg::B_STAGE_BYTES, kb * BLOCK_K, cta_rank * BLOCK_N);
+          tma_load_2d(&p.tmB, bres_bar, smem_b + kb * Cfg::B_STAGE_BYTES, kb * BLOCK_K, 0);
       }
-      for (int tile = t_first; tile < t_limit; tile += t_step) {
-        const int m_tile = kMC ? tile : tile / p.n_tiles, n_tile = kMC ? cta_rank : tile - m_tile * p.n_tiles;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int n = 0, h0 = 0, w0 = 0, h2 = 0, w2 = 0;
         if (kAMode == A_IM2COL || p.a2_im2col) {
-          const int gm = m_tile * BLOCK_M + cta_rank * A_ROWS;
+          const int gm = m_tile * BLOCK_M;
           n = gm / (p.OH * p.OW);
           const int r = gm - n * p.OH * p.OW;
           const int oh = r / p.OW, ow = r - oh * p.OW;
@@ -181,19 +169,11 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
             else
               tma_load_2d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb2 * BLOCK_K, m_tile * BLOCK_M);
           } else if (kAMode == A_TMA) {
-            if (kMC)
-              tma_load_2d_mc(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES + cta_rank * (A_STAGE_BYTES / 2),
-                             kb * BLOCK_K, m_tile * BLOCK_M + cta_rank * A_ROWS, (uint16_t)3);
-            else
-              tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
+            tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
           } else if (kAMode == A_IM2COL) {
             const int r = tap / p.KW, s = tap - r * p.KW;
-            if (kMC)
-              tma_load_im2col_4d_mc(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES + cta_rank * (A_STAGE_BYTES / 2),
-                                    cb * BLOCK_K, w0, h0, n, (uint16_t)s, (uint16_t)r, (uint16_t)3);
-            else
-              tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, cb * BLOCK_K, w0, h0, n,
-                                 (uint16_t)s, (uint16_t)r);
+            tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, cb * BLOCK_K, w0, h0, n,
+                               (uint16_t)s, (uint16_t)r);
             if (++cb == kb_per_tap) { cb = 0; ++tap; }
           }
           if (!kBRes)
@@ -209,8 +189,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const uint64_t a_desc0 = umma_smem_desc_sw128(smem_u32(smem_a));
     const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(smem_b));
     int stage = 0, phase = 0, local = 0;
-    if (kBRes && t_first < t_limit) mbar_wait(bres_bar, 0);
-    for (int tile = t_first; tile < t_limit; tile += t_step, ++local) {
+    if (kBRes && blockIdx.x < total_tiles) mbar_wait(bres_bar, 0);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
@@ -224,8 +204,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k)
             umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-          if (kMC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);  // the slot is free when BOTH CTAs' MMAs retired
-          else umma_commit(&empty_bar[stage]);                     // frees the smem slot when these MMAs retire
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
           if (kb == p.num_kb - 1) umma_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
@@ -242,8 +221,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const int row = q * 32 + lane;
     const bool store_thread = (warp == 2 && leader);
     int local = 0, gc = 0;  // gc: running column-group counter of this CTA (ring position)
-    for (int tile = t_first; tile < t_limit; tile += t_step, ++local) {
-      const int m_tile = kMC ? tile : tile / p.n_tiles, n_tile = kMC ? cta_rank : tile - m_tile * p.n_tiles;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
       bool tmem_ready = false;
 #pragma unroll 1
@@ -322,8 +301,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     // ===================== residual loader =====================
     if (leader && p.has_res) {
       int gc = 0;
-      for (int tile = t_first; tile < t_limit; tile += t_step) {
-        const int m_tile = kMC ? tile : tile / p.n_tiles, n_tile = kMC ? cta_rank : tile - m_tile * p.n_tiles;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         for (int g = 0; g < Cfg::GROUPS; ++g, ++gc) {
           const int slot = gc % RING;
           mbar_wait(&c_free_bar[slot], ((gc / RING) & 1) ^ 1);
@@ -344,8 +323,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const uint32_t row_off = row * 128, sw = row & 7;
     int stage = 0, phase = 0, arr_stage = 0;
     int issued = 0;
-    for (int tile = t_first; tile < t_limit; tile += t_step) {
-      const int m_tile = kMC ? tile : tile / p.n_tiles;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
       const int gm = m_tile * BLOCK_M + row;
       const bool row_ok = gm < p.M;
       int n = 0, oh = 0, ow = 0;
@@ -402,7 +381,6 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
 
   tcgen05_fence_before();
   __syncthreads();
-  if (kMC) cluster_sync_all();  // neither CTA may exit while the peer can still multicast into it / signal its barriers
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
@@ -453,8 +431,7 @@ static int make_tmap_2d(CUtensorMap* m, const void* base, int precision, uint64_
 // NHWC activation as (C, W, H, N) in TMA im2col mode: one load = 128 consecutive output pixels x 64 channels of one
 // filter tap.  Corner arithmetic as in CUTLASS's fprop (conv/collective/detail.hpp compute_{lower,upper}_corner_whd):
 // lower = -pad, upper = pad - (k - 1); traversal stride = conv stride.
-static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, const ConvShape& s_in, bool second,
-                            uint32_t pixels = BLOCK_M) {
+static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, const ConvShape& s_in, bool second) {
   ConvShape s = s_in;
   if (second) { s.H = s_in.H2; s.W = s_in.W2; s.cin = s_in.cin2; s.kh = s.kw = 1; s.stride = s_in.stride2; s.pad = 0; }
   static EncodeIm2colFn enc = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));
@@ -464,7 +441,7 @@ static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, con
   const int lower[2] = {-s.pad, -s.pad};
   const int upper[2] = {s.pad - (s.kw - 1), s.pad - (s.kh - 1)};
   const cuuint32_t estr[4] = {1, (cuuint32_t)s.stride, (cuuint32_t)s.stride, 1};
-  CUresult r = enc(m, tmap_dtype(precision), 4, const_cast<void*>(base), dims, strides, lower, upper, BLOCK_K, pixels,
+  CUresult r = enc(m, tmap_dtype(precision), 4, const_cast<void*>(base), dims, strides, lower, upper, BLOCK_K, BLOCK_M,
                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -524,29 +501,15 @@ static int num_sms() {
   return sms[dev];
 }
 
-template <typename T, int BLOCK_N, int kAMode, bool kBRes = false, bool kMC = false>
+template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
 static int launch_t(const ConvTcParams& p, cudaStream_t st) {
   using Cfg = TcCfg<BLOCK_N, kBRes>;
   static bool configured[MAX_DEVICES] = {};
-  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode, kBRes, kMC>;
+  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode, kBRes>;
   const int dev = current_device();
   if (!configured[dev]) {
     SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
     configured[dev] = true;
-  }
-  if (kMC) {
-    const int pairs = p.m_tiles < num_sms() / 2 ? p.m_tiles : num_sms() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(cta_threads<BLOCK_N, kAMode>());
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    SEMDIFF_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p));
-    return 0;
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
@@ -562,15 +525,10 @@ static int launch_n(const ConvTcParams& p, int block_n, cudaStream_t st) {
     case 128: return launch_t<T, 128, kAMode>(p, st);
     case 64:
       if constexpr (kAMode != A_GATHER) {
-        if (p.multicast) return launch_t<T, 64, kAMode, false, true>(p, st);
         if (p.n_tiles == 1 && p.num_kb <= MAX_RES_KB) return launch_t<T, 64, kAMode, true>(p, st);
       }
       return launch_t<T, 64, kAMode>(p, st);
-    case 32:
-      if constexpr (kAMode != A_GATHER) {
-        if (p.multicast) return launch_t<T, 32, kAMode, true, true>(p, st);
-      }
-      return launch_t<T, 32, kAMode>(p, st);
+    case 32: return launch_t<T, 32, kAMode>(p, st);
   }
   set_error("conv_tc: unsupported BLOCK_N %d", block_n);
   return SEMDIFF_ERR_UNSUPPORTED;
@@ -600,12 +558,7 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   p.M = (int)s.M();
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K;
-  int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
-  // multicast pairs: spatial (k > 1) convs with 64 or 128 output channels, TMA-fed, single activation source
-  static const bool mc_enabled = getenv("SEMDIFF_NO_MULTICAST") == nullptr;
-  p.multicast = mc_enabled && a_mode != A_GATHER && s.cin2 == 0 && s.kh * s.kw > 1 && (s.cout == 64 || s.cout == 128) &&
-                (s.cout != 64 || p.num_kb <= MAX_RES_KB) && p.m_tiles >= 2;
-  if (p.multicast) block_n = s.cout / 2;
+  const int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
   if (block_n == 0) { set_error("conv_tc: cout %d not a multiple of 32", s.cout); return SEMDIFF_ERR_UNSUPPORTED; }
   p.in = in; p.bias = bias; p.has_res = res != nullptr;
   p.H = s.H; p.W = s.W; p.Cin = s.cin; p.OH = s.OH(); p.OW = s.OW(); p.Cout = s.cout;
@@ -616,9 +569,8 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   p.taps = s.kh * s.kw;
   const uint32_t box_cols = block_n < 64 ? block_n : 64;
   int rc = make_tmap_2d(&p.tmB, w, precision, (uint64_t)s.cout, (uint64_t)s.K(), BLOCK_K, (uint32_t)block_n);
-  const uint32_t a_rows = p.multicast ? BLOCK_M / 2 : BLOCK_M;
-  if (rc == 0 && a_mode == A_TMA) rc = make_tmap_2d(&p.tmA, in, precision, (uint64_t)p.M, (uint64_t)s.cin, BLOCK_K, a_rows);
-  if (rc == 0 && a_mode == A_IM2COL) rc = make_tmap_im2col(&p.tmA, in, precision, s, false, a_rows);
+  if (rc == 0 && a_mode == A_TMA) rc = make_tmap_2d(&p.tmA, in, precision, (uint64_t)p.M, (uint64_t)s.cin, BLOCK_K, BLOCK_M);
+  if (rc == 0 && a_mode == A_IM2COL) rc = make_tmap_im2col(&p.tmA, in, precision, s, false);
   p.num_kb1 = p.num_kb;
   p.stride2 = 1;
   if (rc == 0 && s.cin2 != 0) {
