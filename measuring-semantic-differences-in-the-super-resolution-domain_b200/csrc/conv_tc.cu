@@ -21,6 +21,7 @@
 // Pipelines: smem ring full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue),
 //            C ring res_full/c_free (residual loader <-> epilogue/TMA store).
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -552,6 +553,10 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
     return SEMDIFF_ERR_UNSUPPORTED;
   }
   static_assert(sizeof(ConvTcParams) <= sizeof(L->params), "ConvTcLaunch::params too small");
+  // 3x3 / 64 -> 64 convs of the wide early layers: strip kernel (conv3x3_strip.cu); SEMDIFF_NO_STRIP=1 keeps them on
+  // the generic im2col path (A/B testing)
+  static const bool strip_ok = getenv("SEMDIFF_NO_STRIP") == nullptr;
+  if (strip_ok && use_tma && q.res == nullptr && conv_strip_supported(s, precision)) return conv_strip_prepare(L, q, s, precision);
   ConvTcParams& p = *reinterpret_cast<ConvTcParams*>(L->params);
   memset(&p, 0, sizeof(p));
   const int a_mode = a_mode_for(s, use_tma ? SEMDIFF_CONV_TC_TMA : SEMDIFF_CONV_TC_GATHER);
@@ -590,6 +595,7 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
 }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t st) {
+  if (L->a_mode == 100) return conv_strip_launch(L, st);
   const ConvTcParams& p = *reinterpret_cast<const ConvTcParams*>(L->params);
   if (L->precision == SEMDIFF_BF16) return launch_mode<__nv_bfloat16>(p, L->block_n, L->a_mode, st);
   return launch_mode<__half>(p, L->block_n, L->a_mode, st);

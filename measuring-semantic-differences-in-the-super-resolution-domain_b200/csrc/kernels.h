@@ -45,6 +45,10 @@ struct alignas(64) ConvTcLaunch {
 };
 int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& ptr, const ConvShape& s, int precision, bool use_tma);
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream);
+// strip variant for 3x3 stride-1 pad-1 64 -> 64 convs (conv3x3_strip.cu); conv_tc_launch dispatches to it
+bool conv_strip_supported(const ConvShape& s, int precision);
+int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& ptr, const ConvShape& s, int precision);
+int conv_strip_launch(const ConvTcLaunch* L, cudaStream_t stream);
 
 int distance_parts(int hw, int c);
 int launch_distance(const void* act, int n_pairs, int hw, int c, const float* w, int normalize, float* partial,

@@ -41,6 +41,24 @@ def test_conv_tc_tma(case, precision):
     _check(out, ref, precision)
 
 
+STRIP_CASES = [
+    # 3x3 stride-1 pad-1 64 -> 64 (csrc/conv3x3_strip.cu): every strip pitch, ragged row groups, several images
+    (3, 56, 56, 64, 64, 3, 1, 1, False),     # P = 64, 2 output rows per tile
+    (2, 28, 28, 64, 64, 3, 1, 1, False),     # P = 32, 4 rows per tile
+    (5, 14, 14, 64, 64, 3, 1, 1, False),     # P = 16, 8 rows per tile (14 = 8 + 6: ragged)
+    (2, 112, 112, 64, 64, 3, 1, 1, False),   # P = 128, 1 row per tile (CLIP stem geometry)
+    (2, 37, 50, 64, 64, 3, 1, 1, False),     # H odd (ragged last row group), W not a power of two
+    (1, 6, 126, 64, 64, 3, 1, 1, False),     # W + 2 == 128: the widest row the strip holds
+]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", STRIP_CASES)
+def test_conv3x3_strip(case, precision):
+    out, ref = _conv_case(case, precision, _lib.CONV_TC_TMA)
+    _check(out, ref, precision)
+
+
 def test_conv_tc_many_tiles_persistent():
     """More tiles than SMs: exercises the persistent loop, both TMEM accumulator stages and smem ring wrap."""
     case = (8, 56, 56, 64, 256, 1, 1, 0, True)     # M = 25088 -> 196 m-tiles x 1 n-tile
