@@ -19,17 +19,27 @@
 
 namespace semdiff {
 
-constexpr int STRIP_MAX_BYTES = 3 * 128 * 128 + 1024;  // P = 128: 3 rows of 128 pixels (+ slack rows read by the last taps)
-constexpr int STRIP_B_BYTES = 9 * 64 * 128;
-constexpr int STRIP_C_BYTES = 128 * 128;
-constexpr int STRIP_SMEM = 2 * STRIP_MAX_BYTES + STRIP_B_BYTES + 2 * STRIP_C_BYTES + 16 * 8 + 16 + 1024;
+// Two instantiations share the code (64 -> 64 channels, stride 1):
+//   RG = 1: 3x3 pad 1 (ResNet layer1 / CLIP stage 0 and stem convs): strip = RT + 2 rows, 9 taps
+//   RG = 2: KHx1 pad 0 "row-window" stems (4x1 over SEMDIFF_INPUT_S2D_ROW4, 2x1 over ..._ROW2): no overlap between
+//           the taps in W, but every input row feeds KH output rows, so a tile computes RG = 2 output row groups
+//           (two TMEM accumulators) from one strip of 2 * RT + KH - 1 rows: 5 rows instead of 8 for the 7x7 stem.
+template <int RG> struct StripCfg {
+  static constexpr int MAX_STRIP = RG == 1 ? 3 * 128 * 128 + 1024 : 5 * 128 * 128;  // P = 128 worst case (+ slack rows the last 3x3 taps read)
+  static constexpr int B_BYTES = RG == 1 ? 9 * 8192 : 4 * 8192;
+  static constexpr int C_BUFS = RG == 1 ? 2 : 1;
+  static constexpr int C_BYTES = RG * 128 * 128;
+  static constexpr int TMEM_COLS = RG * 128;   // 2 stages x RG accumulators x 64 columns
+  static constexpr int SMEM = 2 * MAX_STRIP + B_BYTES + C_BUFS * C_BYTES + 16 * 8 + 16 + 1024;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
 
 struct alignas(64) StripParams {
   CUtensorMap tmX;  // input NHWC as (C, W, H, N), box (64, P, RT + 2, 1)
   CUtensorMap tmB;  // weights [64, 576], box (64, 64)
   CUtensorMap tmC;  // output [M, 64], box (64, W)
   const float* bias;
-  int H, W, P, RT, n_img, tiles_per_img, relu;
+  int H, W, OH, P, RT, KH, KW, pad, n_img, tiles_per_img, relu;
 };
 static_assert(sizeof(StripParams) <= 896, "ConvTcLaunch::params too small");
 
@@ -40,14 +50,16 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
-template <typename T>
-__global__ void __launch_bounds__(192, 1) conv3x3_strip_kernel(const __grid_constant__ StripParams p) {
+template <typename T, int RG>
+__global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_constant__ StripParams p) {
+  using Cfg = StripCfg<RG>;
+  constexpr int STRIP_MAX_BYTES = Cfg::MAX_STRIP, STRIP_B_BYTES = Cfg::B_BYTES, STRIP_C_BYTES = Cfg::C_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* strip = smem;                                   // [2][STRIP_MAX_BYTES]
-  uint8_t* smem_b = smem + 2 * STRIP_MAX_BYTES;            // [9][64 x 128 B]
-  uint8_t* smem_c = smem_b + STRIP_B_BYTES;                // [2][128 x 128 B]
-  uint64_t* strip_full = reinterpret_cast<uint64_t*>(smem_c + 2 * STRIP_C_BYTES);
+  uint8_t* smem_b = smem + 2 * STRIP_MAX_BYTES;            // [taps][64 x 128 B]
+  uint8_t* smem_c = smem_b + STRIP_B_BYTES;                // [C_BUFS][RG][128 x 128 B]
+  uint64_t* strip_full = reinterpret_cast<uint64_t*>(smem_c + Cfg::C_BUFS * STRIP_C_BYTES);
   uint64_t* strip_empty = strip_full + 2;
   uint64_t* tmem_full = strip_empty + 2;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -57,18 +69,19 @@ __global__ void __launch_bounds__(192, 1) conv3x3_strip_kernel(const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool leader = elect_one();
   const int total_tiles = p.n_img * p.tiles_per_img;
-  const uint32_t strip_bytes = (uint32_t)(p.RT + 2) * p.P * 128;
+  const int taps = p.KH * p.KW;
+  const uint32_t strip_bytes = (uint32_t)(RG * p.RT + p.KH - 1) * p.P * 128;
 
   if (warp == 0 && leader) {
     tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmB); tma_prefetch_desc(&p.tmC);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&strip_full[i], 1); mbar_init(&strip_empty[i], 1);
-      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 8);
     }
     mbar_init(b_bar, 1);
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc<128>(tmem_ptr);
+  if (warp == 1) tmem_alloc<Cfg::TMEM_COLS>(tmem_ptr);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -76,15 +89,15 @@ __global__ void __launch_bounds__(192, 1) conv3x3_strip_kernel(const __grid_cons
 
   if (warp == 0) {
     if (leader) {
-      mbar_arrive_expect_tx(b_bar, STRIP_B_BYTES);
-      for (int t = 0; t < 9; ++t) tma_load_2d(&p.tmB, b_bar, smem_b + t * 8192, t * 64, 0);
+      mbar_arrive_expect_tx(b_bar, taps * 8192);
+      for (int t = 0; t < taps; ++t) tma_load_2d(&p.tmB, b_bar, smem_b + t * 8192, t * 64, 0);
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const int b = local & 1, ph = (local >> 1) & 1;
-        const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT;
+        const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT * RG;
         mbar_wait(&strip_empty[b], ph ^ 1);
         mbar_arrive_expect_tx(&strip_full[b], strip_bytes);
-        tma_load_4d(&p.tmX, &strip_full[b], strip + b * STRIP_MAX_BYTES, 0, -1, oy0 - 1, n);  // halo: OOB -> zeros
+        tma_load_4d(&p.tmX, &strip_full[b], strip + b * STRIP_MAX_BYTES, 0, -p.pad, oy0 - p.pad, n);  // halo: OOB -> zeros
       }
     }
   } else if (warp == 1) {
@@ -98,17 +111,20 @@ __global__ void __launch_bounds__(192, 1) conv3x3_strip_kernel(const __grid_cons
       mbar_wait(&strip_full[b], ph);
       tcgen05_fence_after();
       if (leader) {
-        const uint32_t tmem_d = tmem_base + b * 64;
         const uint32_t sbase = smem_u32(strip + b * STRIP_MAX_BYTES);
 #pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const int r = tap / 3, s = tap - r * 3;
-          // view of the strip shifted by (r rows, s pixels)
-          const uint64_t a_desc = umma_smem_desc_sw128(sbase + (uint32_t)(r * p.P + s) * 128);
+        for (int tap = 0; tap < taps; ++tap) {
+          const int r = tap / p.KW, s = tap - r * p.KW;
           const uint64_t b_desc = b_desc0 + (uint64_t)((tap * 8192) >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (tap | k) != 0 ? 1u : 0u);
+          for (int g = 0; g < RG; ++g) {
+            // view of the strip shifted by (g row groups + r rows, s pixels)
+            const uint64_t a_desc = umma_smem_desc_sw128(sbase + (uint32_t)((g * p.RT + r) * p.P + s) * 128);
+            const uint32_t tmem_d = tmem_base + (b * RG + g) * 64;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (tap | k) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&strip_empty[b]);
         umma_commit(&tmem_full[b]);
@@ -116,52 +132,60 @@ __global__ void __launch_bounds__(192, 1) conv3x3_strip_kernel(const __grid_cons
       __syncwarp();
     }
   } else {
-    // epilogue: virtual pixel v = oy * P + ox -> one staged 128-byte row; one TMA store per output image row
+    // epilogue, 8 warps = 4 TMEM lane quarters x 2: the second set of four takes the second row group (RG = 2) or the
+    // second half of the channels (RG = 1).  Virtual pixel v = oy * P + ox -> one staged 128-byte row; one TMA store
+    // per output image row.
     const int q = warp & 3, v = q * 32 + lane;
+    const int set = (warp - 2) >> 2;
     const bool store_thread = (warp == 2 && leader);
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int b = local & 1, ph = (local >> 1) & 1;
-      const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT;
-      uint8_t* cbuf = smem_c + b * STRIP_C_BYTES;
-      if (store_thread) bulk_wait_read<1>();
-      named_bar_sync(1, 128);
+      const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT * RG;
+      uint8_t* cbuf = smem_c + (Cfg::C_BUFS == 2 ? b : 0) * STRIP_C_BYTES;
+      if (store_thread) bulk_wait_read<Cfg::C_BUFS - 1>();
+      named_bar_sync(1, 256);
       mbar_wait_backoff(&tmem_full[b], ph);
       tcgen05_fence_after();
-      const uint32_t row_addr = smem_u32(cbuf) + v * 128;
+      const int g_lo = RG == 2 ? set : 0, g_hi = RG == 2 ? set + 1 : 1;
+      const int u_lo = RG == 2 ? 0 : set, u_hi = RG == 2 ? 2 : set + 1;
 #pragma unroll 1
-      for (int u = 0; u < 2; ++u) {
-        uint32_t acc[32];
-        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + b * 64 + u * 32, acc);
-        tmem_ld_wait();
-        if (u == 1) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[b]);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int c0 = u * 32 + j * 8;
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
-          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
-          float f[8] = {__uint_as_float(acc[j * 8 + 0]) + b0.x, __uint_as_float(acc[j * 8 + 1]) + b0.y,
-                        __uint_as_float(acc[j * 8 + 2]) + b0.z, __uint_as_float(acc[j * 8 + 3]) + b0.w,
-                        __uint_as_float(acc[j * 8 + 4]) + b1.x, __uint_as_float(acc[j * 8 + 5]) + b1.y,
-                        __uint_as_float(acc[j * 8 + 6]) + b1.z, __uint_as_float(acc[j * 8 + 7]) + b1.w};
-          if (p.relu) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+      for (int g = g_lo; g < g_hi; ++g) {
+        const uint32_t row_addr = smem_u32(cbuf + g * 128 * 128) + v * 128;
+#pragma unroll 1
+        for (int u = u_lo; u < u_hi; ++u) {
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + (b * RG + g) * 64 + u * 32, acc);
+          tmem_ld_wait();
+          if (g == g_hi - 1 && u == u_hi - 1) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[b]);
           }
-          const uint4 o = pack8<T>(f);
-          const uint32_t addr = row_addr + ((uint32_t)((u * 4 + j) ^ (v & 7)) << 4);
-          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c0 = u * 32 + j * 8;
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
+            float f[8] = {__uint_as_float(acc[j * 8 + 0]) + b0.x, __uint_as_float(acc[j * 8 + 1]) + b0.y,
+                          __uint_as_float(acc[j * 8 + 2]) + b0.z, __uint_as_float(acc[j * 8 + 3]) + b0.w,
+                          __uint_as_float(acc[j * 8 + 4]) + b1.x, __uint_as_float(acc[j * 8 + 5]) + b1.y,
+                          __uint_as_float(acc[j * 8 + 6]) + b1.z, __uint_as_float(acc[j * 8 + 7]) + b1.w};
+            if (p.relu) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+            }
+            const uint4 o = pack8<T>(f);
+            const uint32_t addr = row_addr + ((uint32_t)((u * 4 + j) ^ (v & 7)) << 4);
+            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (store_thread) {
-        for (int oy = 0; oy < p.RT; ++oy)
-          if (oy0 + oy < p.H) tma_store_2d(&p.tmC, cbuf + oy * p.P * 128, 0, (n * p.H + oy0 + oy) * p.W);
+        for (int oy = 0; oy < RG * p.RT; ++oy)
+          if (oy0 + oy < p.OH) tma_store_2d(&p.tmC, cbuf + oy * p.P * 128, 0, (n * p.OH + oy0 + oy) * p.W);
         bulk_commit();
       }
     }
@@ -171,7 +195,7 @@ __global__ void __launch_bounds__(192, 1) conv3x3_strip_kernel(const __grid_cons
   __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc<128>(tmem_base);
+    tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -180,9 +204,12 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+static bool strip_is_3x3(const ConvShape& s) { return s.kh == 3 && s.kw == 3 && s.pad == 1; }
+static bool strip_is_rowwin(const ConvShape& s) { return s.kw == 1 && s.kh >= 2 && s.kh <= 4 && s.pad == 0; }
 bool conv_strip_supported(const ConvShape& s, int precision) {
-  return (precision == SEMDIFF_BF16 || precision == SEMDIFF_FP16) && s.kh == 3 && s.kw == 3 && s.stride == 1 && s.pad == 1 &&
-         s.cin == 64 && s.cout == 64 && s.cin2 == 0 && s.W + 2 <= 128 && s.W >= 6 && (int64_t)s.n_img * s.H * s.W < ((int64_t)1 << 31);
+  return (precision == SEMDIFF_BF16 || precision == SEMDIFF_FP16) && (strip_is_3x3(s) || strip_is_rowwin(s)) && s.stride == 1 &&
+         s.cin == 64 && s.cout == 64 && s.cin2 == 0 && s.W + s.kw - 1 <= 128 && s.W >= 6 && s.OH() >= 1 &&
+         (int64_t)s.n_img * s.H * s.W < ((int64_t)1 << 31);
 }
 
 int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision) {
@@ -197,23 +224,25 @@ int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, i
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return SEMDIFF_ERR_CUDA; }
   StripParams& p = *reinterpret_cast<StripParams*>(L->params);
   memset(&p, 0, sizeof(p));
+  const int RG = strip_is_rowwin(s) ? 2 : 1;
   int P = 16;
-  while (P < s.W + 2) P <<= 1;
-  p.P = P; p.RT = 128 / P; p.H = s.H; p.W = s.W; p.n_img = s.n_img; p.relu = s.relu; p.bias = q.bias;
-  p.tiles_per_img = (s.H + p.RT - 1) / p.RT;
+  while (P < s.W + s.kw - 1) P <<= 1;
+  p.P = P; p.RT = 128 / P; p.H = s.H; p.W = s.W; p.OH = s.OH(); p.KH = s.kh; p.KW = s.kw; p.pad = s.pad;
+  p.n_img = s.n_img; p.relu = s.relu; p.bias = q.bias;
+  p.tiles_per_img = (p.OH + p.RT * RG - 1) / (p.RT * RG);
   const CUtensorMapDataType dt = precision == SEMDIFF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
     const cuuint64_t dims[4] = {64, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.n_img};
     const cuuint64_t strides[3] = {128, (cuuint64_t)s.W * 128, (cuuint64_t)s.H * s.W * 128};
-    const cuuint32_t box[4] = {64, (cuuint32_t)P, (cuuint32_t)(p.RT + 2), 1};
+    const cuuint32_t box[4] = {64, (cuuint32_t)P, (cuuint32_t)(RG * p.RT + s.kh - 1), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.tmX, dt, 4, const_cast<void*>(q.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: strip tensor map failed (%d) W=%d H=%d P=%d", (int)r, s.W, s.H, P); return SEMDIFF_ERR_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {576, 64};
-    const cuuint64_t strides[1] = {576 * 2};
+    const cuuint64_t dims[2] = {(cuuint64_t)s.K(), 64};
+    const cuuint64_t strides[1] = {(cuuint64_t)s.K() * 2};
     const cuuint32_t box[2] = {64, 64};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmB, dt, 2, const_cast<void*>(q.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -221,7 +250,7 @@ int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, i
     if (r != CUDA_SUCCESS) { set_error("conv_strip: weight tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {64, (cuuint64_t)s.n_img * s.H * s.W};
+    const cuuint64_t dims[2] = {64, (cuuint64_t)s.n_img * p.OH * s.W};
     const cuuint64_t strides[1] = {128};
     const cuuint32_t box[2] = {64, (cuuint32_t)s.W};
     const cuuint32_t estr[2] = {1, 1};
@@ -229,28 +258,32 @@ int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, i
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: output tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
-  L->block_n = 64; L->a_mode = 100; L->precision = precision;  // a_mode 100 = strip kernel
+  L->block_n = 64; L->a_mode = 100 + RG; L->precision = precision;  // a_mode 101 / 102 = strip kernel, RG = 1 / 2
+  return 0;
+}
+
+template <typename T, int RG>
+static int strip_launch_t(const StripParams& p, int dev, int sms, cudaStream_t st) {
+  static bool configured[64] = {};
+  if (!configured[dev]) {
+    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(conv3x3_strip_kernel<T, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripCfg<RG>::SMEM));
+    configured[dev] = true;
+  }
+  const int tiles = p.n_img * p.tiles_per_img;
+  conv3x3_strip_kernel<T, RG><<<tiles < sms ? tiles : sms, 320, StripCfg<RG>::SMEM, st>>>(p);
+  SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
 
 int conv_strip_launch(const ConvTcLaunch* L, cudaStream_t st) {
   const StripParams& p = *reinterpret_cast<const StripParams*>(L->params);
-  static bool configured[64] = {};
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (dev < 0 || dev >= 64) dev = 0;
-  if (!configured[dev]) {
-    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(conv3x3_strip_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM));
-    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(conv3x3_strip_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, STRIP_SMEM));
-    configured[dev] = true;
-  }
-  const int tiles = p.n_img * p.tiles_per_img;
-  const int grid = tiles < sms ? tiles : sms;
-  if (L->precision == SEMDIFF_BF16) conv3x3_strip_kernel<__nv_bfloat16><<<grid, 192, STRIP_SMEM, st>>>(p);
-  else conv3x3_strip_kernel<__half><<<grid, 192, STRIP_SMEM, st>>>(p);
-  SEMDIFF_CUDA_OK(cudaGetLastError());
-  return 0;
+  const bool bf = L->precision == SEMDIFF_BF16;
+  if (L->a_mode == 102) return bf ? strip_launch_t<__nv_bfloat16, 2>(p, dev, sms, st) : strip_launch_t<__half, 2>(p, dev, sms, st);
+  return bf ? strip_launch_t<__nv_bfloat16, 1>(p, dev, sms, st) : strip_launch_t<__half, 1>(p, dev, sms, st);
 }
 
 }  // namespace semdiff

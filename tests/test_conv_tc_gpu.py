@@ -59,6 +59,22 @@ def test_conv3x3_strip(case, precision):
     _check(out, ref, precision)
 
 
+@pytest.mark.parametrize("geom", [(2, 115, 112, 4), (3, 59, 56, 4), (2, 113, 112, 2), (1, 20, 14, 3), (2, 12, 126, 4)])
+def test_conv_rowwindow_strip(geom):
+    """KH x 1 pad-0 'row-window' stems (4x1 over the S2D_ROW4 input, 2x1 over S2D_ROW2): strip kernel, RG = 2."""
+    import torch
+    from helpers import conv2d, conv_reference
+    n, H, W, kh = geom
+    g = torch.Generator(device="cuda").manual_seed(11)
+    x = torch.randn(n, H, W, 64, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(64, kh, 1, 64, device="cuda", generator=g) * (2.0 / (kh * 64)) ** 0.5).bfloat16()
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    # the helper takes one padding for both axes: 0 here
+    out = conv2d(x, w, b, None, 1, 0, True, "bf16", _lib.CONV_TC_TMA).double()
+    ref = torch.relu(torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(0, 3, 1, 2), b.double())).permute(0, 2, 3, 1)
+    _check(out, ref, "bf16")
+
+
 def test_conv_tc_many_tiles_persistent():
     """More tiles than SMs: exercises the persistent loop, both TMEM accumulator stages and smem ring wrap."""
     case = (8, 56, 56, 64, 256, 1, 1, 0, True)     # M = 25088 -> 196 m-tiles x 1 n-tile
