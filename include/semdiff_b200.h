@@ -44,7 +44,9 @@ enum {
 enum {
   SEMDIFF_INPUT_NHWC8 = 0,    /* [2n, H, W, 8], channels 3..7 zero */
   SEMDIFF_INPUT_S2D_ROW4 = 1, /* [2n, H/2+3, W/2, 64]: 2x2 space-to-depth row windows for 7x7/2 pad-3 stems (elementwise.cu) */
-  SEMDIFF_INPUT_S2D_ROW2 = 2  /* [2n, H/2+1, W/2, 64]: the same for 3x3/2 pad-1 stems (window of 2, upper 32 channels zero) */
+  SEMDIFF_INPUT_S2D_ROW2 = 2, /* [2n, H/2+1, W/2, 64]: the same for 3x3/2 pad-1 stems (window of 2, upper 32 channels zero) */
+  SEMDIFF_INPUT_S2D16 = 3     /* [2n, H/2, W/2, 16]: plain 2x2 space-to-depth, channel (dy*2+dx)*3+ci, 12..15 zero; a 7x7/2
+                                 pad-3 stem is a 4x4 stride-1 conv over it with padding 2 before / 1 after */
 };
 
 /* One step of the trunk program.  Buffers are logical ids in [0, n_bufs); buffer 0 is the packed
@@ -67,6 +69,7 @@ typedef struct semdiff_op {
   int32_t src2;      /* CONV: second input buffer read through a fused 1x1 conv (projection shortcut), or -1 */
   int32_t cin2;      /* channels of src2; weight rows are [kh*kw*cin | cin2] */
   int32_t stride2;   /* spatial stride of the fused 1x1 conv over src2 */
+  int32_t pad_hi;    /* CONV: padding after the last row/column if it differs from `pad`, else -1 (symmetric) */
   const void* weight; /* device, [cout][kh][kw][cin] in the plan's precision */
   const float* bias;  /* device, [cout] fp32 (folded BN shift) */
 } semdiff_op;
@@ -115,11 +118,11 @@ int semdiff_pack_input(const void* gt, const void* sr, int32_t in_precision, int
                        void* out, int32_t precision, int32_t layout, semdiff_stream_t stream);
 
 /* out = act(conv(in, weight[:, :kh*kw*cin]) (+ conv1x1_stride2(in2, weight[:, kh*kw*cin:])) + bias (+ residual));
- * NHWC; in2 may be NULL; impl = SEMDIFF_CONV_* */
+ * NHWC; in2 may be NULL; pad_hi = padding after the last row/column (-1: same as pad); impl = SEMDIFF_CONV_* */
 int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out,
                    int32_t n_img, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw,
                    int32_t stride, int32_t pad, int32_t relu, const void* in2, int32_t H2, int32_t W2, int32_t cin2,
-                   int32_t stride2, int32_t precision, int32_t impl, semdiff_stream_t stream);
+                   int32_t stride2, int32_t pad_hi, int32_t precision, int32_t impl, semdiff_stream_t stream);
 
 int semdiff_maxpool3x3s2(const void* in, void* out, int32_t n_img, int32_t H, int32_t W, int32_t c,
                          int32_t precision, semdiff_stream_t stream);

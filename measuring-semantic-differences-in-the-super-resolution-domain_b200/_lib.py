@@ -14,14 +14,14 @@ PRECISIONS = {"bf16": BF16, "fp16": FP16, "fp32": FP32}
 CONV_AUTO, CONV_SIMT, CONV_TC_GATHER, CONV_TC_TMA = 0, 1, 2, 3
 OP_CONV, OP_MAXPOOL3S2, OP_AVGPOOL, OP_TAP = 0, 1, 2, 3
 MAX_PARTS = 64
-INPUT_NHWC8, INPUT_S2D_ROW4, INPUT_S2D_ROW2 = 0, 1, 2
+INPUT_NHWC8, INPUT_S2D_ROW4, INPUT_S2D_ROW2, INPUT_S2D16 = 0, 1, 2, 3
 
 
 class SemdiffOp(C.Structure):
     _fields_ = [("kind", C.c_int32), ("src", C.c_int32), ("dst", C.c_int32), ("res", C.c_int32),
                 ("cin", C.c_int32), ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("stride", C.c_int32), ("pad", C.c_int32), ("relu", C.c_int32), ("tap", C.c_int32),
-                ("src2", C.c_int32), ("cin2", C.c_int32), ("stride2", C.c_int32),
+                ("src2", C.c_int32), ("cin2", C.c_int32), ("stride2", C.c_int32), ("pad_hi", C.c_int32),
                 ("weight", C.c_void_p), ("bias", C.c_void_p)]
 
 
@@ -37,7 +37,7 @@ SIGNATURES = {
     "semdiff_plan_get_profile": (_I, [_P, C.POINTER(C.c_float), C.POINTER(_I), _I, _I]),
     "semdiff_plan_last_launches": (_L, [_P]),
     "semdiff_pack_input": (_I, [_P, _P, _I, _I, _I, _I, _P, _I, _I, _P]),
-    "semdiff_conv2d": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "semdiff_conv2d": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "semdiff_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_distance_parts": (_I, [_I, _I]),

@@ -24,10 +24,15 @@ namespace semdiff {
 //   RG = 2: KHx1 pad 0 "row-window" stems (4x1 over SEMDIFF_INPUT_S2D_ROW4, 2x1 over ..._ROW2): no overlap between
 //           the taps in W, but every input row feeds KH output rows, so a tile computes RG = 2 output row groups
 //           (two TMEM accumulators) from one strip of 2 * RT + KH - 1 rows: 5 rows instead of 8 for the 7x7 stem.
-template <int RG> struct StripCfg {
-  static constexpr int MAX_STRIP = RG == 1 ? 3 * 128 * 128 + 1024 : 5 * 128 * 128;  // P = 128 worst case (+ slack rows the last 3x3 taps read)
-  static constexpr int B_BYTES = RG == 1 ? 9 * 8192 : 4 * 8192;
-  static constexpr int C_BUFS = RG == 1 ? 2 : 1;
+//   RG = 4, ROWB = 32: the same (four row groups per strip) with 16-channel pixels (SEMDIFF_INPUT_S2D16, 32-byte rows, SWIZZLE_32B, one K = 16 MMA
+//           per tap): the 7x7/2 stem as a 4x4 conv (pad 2 before / 1 after) whose 16 taps are views shifted by
+//           (r rows, j pixels) - the 4x window expansion of the row-window layouts is never materialised.
+template <int RG, int ROWB = 128> struct StripCfg {
+  // P = 128 worst case; + slack for the rows that taps shifted in W read beyond the strip (not needed for KW = 1)
+  static constexpr int MAX_STRIP = (RG == 1 ? 3 : RG + 3) * 128 * ROWB + ((RG == 1 || ROWB == 32) ? 1024 : 0);
+  static constexpr int B_TAP_BYTES = 64 * ROWB;
+  static constexpr int B_BYTES = (RG == 1 ? 9 : (ROWB == 32 ? 16 : 4)) * B_TAP_BYTES;
+  static constexpr int C_BUFS = (RG == 1 || ROWB == 32) ? 2 : 1;  // the 64-channel row-window variant has no room for two
   static constexpr int C_BYTES = RG * 128 * 128;
   static constexpr int TMEM_COLS = RG * 128;   // 2 stages x RG accumulators x 64 columns
   static constexpr int SMEM = 2 * MAX_STRIP + B_BYTES + C_BUFS * C_BYTES + 16 * 8 + 16 + 1024;
@@ -39,7 +44,7 @@ struct alignas(64) StripParams {
   CUtensorMap tmB;  // weights [64, 576], box (64, 64)
   CUtensorMap tmC;  // output [M, 64], box (64, W)
   const float* bias;
-  int H, W, OH, P, RT, KH, KW, pad, n_img, tiles_per_img, relu;
+  int H, W, OH, OW, P, RT, KH, KW, pad, n_img, tiles_per_img, relu;
 };
 static_assert(sizeof(StripParams) <= 896, "ConvTcLaunch::params too small");
 
@@ -50,9 +55,22 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
       : "memory");
 }
 
-template <typename T, int RG>
+// K-major operand descriptor for ROWB-byte rows: 128B swizzle (8-row groups 1024 B apart) or 32B swizzle (256 B apart)
+template <int ROWB> __device__ __forceinline__ uint64_t strip_desc(uint32_t smem_addr) {
+  if constexpr (ROWB == 128) return umma_smem_desc_sw128(smem_addr);
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;   // SBO: 8 rows x 32 B
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;          // SWIZZLE_32B
+  return d;
+}
+
+template <typename T, int RG, int ROWB>
 __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_constant__ StripParams p) {
-  using Cfg = StripCfg<RG>;
+  using Cfg = StripCfg<RG, ROWB>;
+  constexpr int KSTEPS = ROWB / 32;   // K = 16 MMAs per tap
   constexpr int STRIP_MAX_BYTES = Cfg::MAX_STRIP, STRIP_B_BYTES = Cfg::B_BYTES, STRIP_C_BYTES = Cfg::C_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -70,7 +88,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
   const bool leader = elect_one();
   const int total_tiles = p.n_img * p.tiles_per_img;
   const int taps = p.KH * p.KW;
-  const uint32_t strip_bytes = (uint32_t)(RG * p.RT + p.KH - 1) * p.P * 128;
+  const uint32_t strip_bytes = (uint32_t)(RG * p.RT + p.KH - 1) * p.P * ROWB;
 
   if (warp == 0 && leader) {
     tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmB); tma_prefetch_desc(&p.tmC);
@@ -89,8 +107,8 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
 
   if (warp == 0) {
     if (leader) {
-      mbar_arrive_expect_tx(b_bar, taps * 8192);
-      for (int t = 0; t < taps; ++t) tma_load_2d(&p.tmB, b_bar, smem_b + t * 8192, t * 64, 0);
+      mbar_arrive_expect_tx(b_bar, taps * Cfg::B_TAP_BYTES);
+      for (int t = 0; t < taps; ++t) tma_load_2d(&p.tmB, b_bar, smem_b + t * Cfg::B_TAP_BYTES, t * (ROWB / 2), 0);
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const int b = local & 1, ph = (local >> 1) & 1;
@@ -102,7 +120,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = umma_idesc_f16(Elem<T>::kUmmaFormat, 128, 64);
-    const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(smem_b));
+    const uint64_t b_desc0 = strip_desc<ROWB>(smem_u32(smem_b));
     int local = 0;
     if (blockIdx.x < total_tiles) mbar_wait(b_bar, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
@@ -115,14 +133,14 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
 #pragma unroll 1
         for (int tap = 0; tap < taps; ++tap) {
           const int r = tap / p.KW, s = tap - r * p.KW;
-          const uint64_t b_desc = b_desc0 + (uint64_t)((tap * 8192) >> 4);
+          const uint64_t b_desc = b_desc0 + (uint64_t)((tap * Cfg::B_TAP_BYTES) >> 4);
 #pragma unroll
           for (int g = 0; g < RG; ++g) {
             // view of the strip shifted by (g row groups + r rows, s pixels)
-            const uint64_t a_desc = umma_smem_desc_sw128(sbase + (uint32_t)((g * p.RT + r) * p.P + s) * 128);
+            const uint64_t a_desc = strip_desc<ROWB>(sbase + (uint32_t)((g * p.RT + r) * p.P + s) * ROWB);
             const uint32_t tmem_d = tmem_base + (b * RG + g) * 64;
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int k = 0; k < KSTEPS; ++k)
               umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (tap | k) != 0 ? 1u : 0u);
           }
         }
@@ -133,7 +151,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
     }
   } else {
     // epilogue, 8 warps = 4 TMEM lane quarters x 2: the second set of four takes the second row group (RG = 2) or the
-    // second half of the channels (RG = 1).  Virtual pixel v = oy * P + ox -> one staged 128-byte row; one TMA store
+    // second half of the channels (RG = 1); with RG = 4 each set takes two row groups.  Virtual pixel v = oy * P + ox -> one staged 128-byte row; one TMA store
     // per output image row.
     const int q = warp & 3, v = q * 32 + lane;
     const int set = (warp - 2) >> 2;
@@ -147,8 +165,8 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       named_bar_sync(1, 256);
       mbar_wait_backoff(&tmem_full[b], ph);
       tcgen05_fence_after();
-      const int g_lo = RG == 2 ? set : 0, g_hi = RG == 2 ? set + 1 : 1;
-      const int u_lo = RG == 2 ? 0 : set, u_hi = RG == 2 ? 2 : set + 1;
+      const int g_lo = RG >= 2 ? set * (RG / 2) : 0, g_hi = RG >= 2 ? g_lo + RG / 2 : 1;
+      const int u_lo = RG >= 2 ? 0 : set, u_hi = RG >= 2 ? 2 : set + 1;
 #pragma unroll 1
       for (int g = g_lo; g < g_hi; ++g) {
         const uint32_t row_addr = smem_u32(cbuf + g * 128 * 128) + v * 128;
@@ -185,7 +203,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       named_bar_sync(1, 256);
       if (store_thread) {
         for (int oy = 0; oy < RG * p.RT; ++oy)
-          if (oy0 + oy < p.OH) tma_store_2d(&p.tmC, cbuf + oy * p.P * 128, 0, (n * p.OH + oy0 + oy) * p.W);
+          if (oy0 + oy < p.OH) tma_store_2d(&p.tmC, cbuf + oy * p.P * 128, 0, (n * p.OH + oy0 + oy) * p.OW);
         bulk_commit();
       }
     }
@@ -204,11 +222,12 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool strip_is_3x3(const ConvShape& s) { return s.kh == 3 && s.kw == 3 && s.pad == 1; }
-static bool strip_is_rowwin(const ConvShape& s) { return s.kw == 1 && s.kh >= 2 && s.kh <= 4 && s.pad == 0; }
+static bool strip_is_3x3(const ConvShape& s) { return s.cin == 64 && s.kh == 3 && s.kw == 3 && s.pad == 1 && s.pad_after() == 1; }
+static bool strip_is_rowwin(const ConvShape& s) { return s.cin == 64 && s.kw == 1 && s.kh >= 2 && s.kh <= 4 && s.pad == 0 && s.pad_after() == 0; }
+static bool strip_is_s2d16(const ConvShape& s) { return s.cin == 16 && s.kh == 4 && s.kw == 4 && s.pad == 2 && s.pad_after() == 1; }
 bool conv_strip_supported(const ConvShape& s, int precision) {
-  return (precision == SEMDIFF_BF16 || precision == SEMDIFF_FP16) && (strip_is_3x3(s) || strip_is_rowwin(s)) && s.stride == 1 &&
-         s.cin == 64 && s.cout == 64 && s.cin2 == 0 && s.W + s.kw - 1 <= 128 && s.W >= 6 && s.OH() >= 1 &&
+  return (precision == SEMDIFF_BF16 || precision == SEMDIFF_FP16) && (strip_is_3x3(s) || strip_is_rowwin(s) || strip_is_s2d16(s)) &&
+         s.stride == 1 && s.cout == 64 && s.cin2 == 0 && s.OW() + s.kw - 1 <= 128 && s.W >= 6 && s.OH() >= 1 &&
          (int64_t)s.n_img * s.H * s.W < ((int64_t)1 << 31);
 }
 
@@ -224,53 +243,57 @@ int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, i
   if (enc == nullptr) { set_error("cuTensorMapEncodeTiled entry point not found"); return SEMDIFF_ERR_CUDA; }
   StripParams& p = *reinterpret_cast<StripParams*>(L->params);
   memset(&p, 0, sizeof(p));
-  const int RG = strip_is_rowwin(s) ? 2 : 1;
+  const int RG = strip_is_3x3(s) ? 1 : (strip_is_s2d16(s) ? 4 : 2);
+  const int ROWB = s.cin * 2;
   int P = 16;
-  while (P < s.W + s.kw - 1) P <<= 1;
-  p.P = P; p.RT = 128 / P; p.H = s.H; p.W = s.W; p.OH = s.OH(); p.KH = s.kh; p.KW = s.kw; p.pad = s.pad;
+  while (P < s.OW() + s.kw - 1) P <<= 1;
+  p.P = P; p.RT = 128 / P; p.H = s.H; p.W = s.W; p.OH = s.OH(); p.OW = s.OW(); p.KH = s.kh; p.KW = s.kw; p.pad = s.pad;
   p.n_img = s.n_img; p.relu = s.relu; p.bias = q.bias;
   p.tiles_per_img = (p.OH + p.RT * RG - 1) / (p.RT * RG);
   const CUtensorMapDataType dt = precision == SEMDIFF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
-    const cuuint64_t dims[4] = {64, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.n_img};
-    const cuuint64_t strides[3] = {128, (cuuint64_t)s.W * 128, (cuuint64_t)s.H * s.W * 128};
-    const cuuint32_t box[4] = {64, (cuuint32_t)P, (cuuint32_t)(RG * p.RT + s.kh - 1), 1};
+    const CUtensorMapSwizzle swz = ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+    const cuuint64_t dims[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.n_img};
+    const cuuint64_t strides[3] = {(cuuint64_t)ROWB, (cuuint64_t)s.W * ROWB, (cuuint64_t)s.H * s.W * ROWB};
+    const cuuint32_t box[4] = {(cuuint32_t)s.cin, (cuuint32_t)P, (cuuint32_t)(RG * p.RT + s.kh - 1), 1};
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.tmX, dt, 4, const_cast<void*>(q.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: strip tensor map failed (%d) W=%d H=%d P=%d", (int)r, s.W, s.H, P); return SEMDIFF_ERR_CUDA; }
   }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)s.K(), 64};
     const cuuint64_t strides[1] = {(cuuint64_t)s.K() * 2};
-    const cuuint32_t box[2] = {64, 64};
+    const cuuint32_t box[2] = {(cuuint32_t)s.cin, 64};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmB, dt, 2, const_cast<void*>(q.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: weight tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {64, (cuuint64_t)s.n_img * p.OH * s.W};
+    const cuuint64_t dims[2] = {64, (cuuint64_t)s.n_img * p.OH * p.OW};
     const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {64, (cuuint32_t)s.W};
+    const cuuint32_t box[2] = {64, (cuuint32_t)p.OW};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmC, dt, 2, q.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: output tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
-  L->block_n = 64; L->a_mode = 100 + RG; L->precision = precision;  // a_mode 101 / 102 = strip kernel, RG = 1 / 2
+  L->block_n = 64; L->a_mode = ROWB == 32 ? 103 : 100 + RG; L->precision = precision;  // 101 / 102: 64-channel strips, RG = 1 / 2; 103: 16-channel
   return 0;
 }
 
-template <typename T, int RG>
+template <typename T, int RG, int ROWB>
 static int strip_launch_t(const StripParams& p, int dev, int sms, cudaStream_t st) {
   static bool configured[64] = {};
+  auto kern = conv3x3_strip_kernel<T, RG, ROWB>;
   if (!configured[dev]) {
-    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(conv3x3_strip_kernel<T, RG>, cudaFuncAttributeMaxDynamicSharedMemorySize, StripCfg<RG>::SMEM));
+    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StripCfg<RG, ROWB>::SMEM));
     configured[dev] = true;
   }
   const int tiles = p.n_img * p.tiles_per_img;
-  conv3x3_strip_kernel<T, RG><<<tiles < sms ? tiles : sms, 320, StripCfg<RG>::SMEM, st>>>(p);
+  kern<<<tiles < sms ? tiles : sms, 320, StripCfg<RG, ROWB>::SMEM, st>>>(p);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -282,8 +305,11 @@ int conv_strip_launch(const ConvTcLaunch* L, cudaStream_t st) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (dev < 0 || dev >= 64) dev = 0;
   const bool bf = L->precision == SEMDIFF_BF16;
-  if (L->a_mode == 102) return bf ? strip_launch_t<__nv_bfloat16, 2>(p, dev, sms, st) : strip_launch_t<__half, 2>(p, dev, sms, st);
-  return bf ? strip_launch_t<__nv_bfloat16, 1>(p, dev, sms, st) : strip_launch_t<__half, 1>(p, dev, sms, st);
+  switch (L->a_mode) {
+    case 103: return bf ? strip_launch_t<__nv_bfloat16, 4, 32>(p, dev, sms, st) : strip_launch_t<__half, 4, 32>(p, dev, sms, st);
+    case 102: return bf ? strip_launch_t<__nv_bfloat16, 2, 128>(p, dev, sms, st) : strip_launch_t<__half, 2, 128>(p, dev, sms, st);
+  }
+  return bf ? strip_launch_t<__nv_bfloat16, 1, 128>(p, dev, sms, st) : strip_launch_t<__half, 1, 128>(p, dev, sms, st);
 }
 
 }  // namespace semdiff

@@ -477,6 +477,7 @@ static int a_mode_for(const ConvShape& s, int requested) {
 
 bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma) {
   if (precision != SEMDIFF_BF16 && precision != SEMDIFF_FP16) return false;
+  if (s.pad_hi >= 0 && s.pad_hi != s.pad) return false;  // asymmetric padding: strip kernel or SIMT only
   if (s.cin % 8 != 0 || s.cout % 32 != 0) return false;
   if (s.cin > 64 && s.cin % 64 != 0) return false;
   if (s.cin < 64 && 64 % s.cin != 0) return false;
@@ -546,6 +547,10 @@ static int launch_mode(const ConvTcParams& p, int block_n, int a_mode, cudaStrea
 }
 
 int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision, bool use_tma) {
+  // 64 -> 64 spatial convs of the wide early layers and the space-to-depth stems: strip kernel (conv3x3_strip.cu);
+  // SEMDIFF_NO_STRIP=1 keeps them on the generic im2col path (A/B testing)
+  static const bool strip_ok = getenv("SEMDIFF_NO_STRIP") == nullptr;
+  if ((strip_ok || s.cin < 64) && use_tma && q.res == nullptr && conv_strip_supported(s, precision)) return conv_strip_prepare(L, q, s, precision);
   const void* in = q.in; const void* w = q.w; const float* bias = q.bias; const void* res = q.res; void* out = q.out;
   if (!conv_tc_supported(s, precision, use_tma)) {
     set_error("conv_tc: unsupported shape cin=%d cout=%d k=%dx%d stride=%d pad=%d tma=%d precision=%d", s.cin, s.cout,
@@ -553,10 +558,6 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
     return SEMDIFF_ERR_UNSUPPORTED;
   }
   static_assert(sizeof(ConvTcParams) <= sizeof(L->params), "ConvTcLaunch::params too small");
-  // 3x3 / 64 -> 64 convs of the wide early layers: strip kernel (conv3x3_strip.cu); SEMDIFF_NO_STRIP=1 keeps them on
-  // the generic im2col path (A/B testing)
-  static const bool strip_ok = getenv("SEMDIFF_NO_STRIP") == nullptr;
-  if (strip_ok && use_tma && q.res == nullptr && conv_strip_supported(s, precision)) return conv_strip_prepare(L, q, s, precision);
   ConvTcParams& p = *reinterpret_cast<ConvTcParams*>(L->params);
   memset(&p, 0, sizeof(p));
   const int a_mode = a_mode_for(s, use_tma ? SEMDIFF_CONV_TC_TMA : SEMDIFF_CONV_TC_GATHER);

@@ -13,8 +13,10 @@ namespace semdiff {
 struct ConvShape {
   int n_img, H, W, cin, cout, kh, kw, stride, pad, relu;
   int cin2 = 0, stride2 = 1, H2 = 0, W2 = 0;
-  int OH() const { return (H + 2 * pad - kh) / stride + 1; }
-  int OW() const { return (W + 2 * pad - kw) / stride + 1; }
+  int pad_hi = -1;  // padding after the last row / column when it differs from `pad` (-1: symmetric)
+  int pad_after() const { return pad_hi < 0 ? pad : pad_hi; }
+  int OH() const { return (H + pad + pad_after() - kh) / stride + 1; }
+  int OW() const { return (W + pad + pad_after() - kw) / stride + 1; }
   int64_t M() const { return (int64_t)n_img * OH() * OW(); }
   int K1() const { return kh * kw * cin; }
   int K() const { return kh * kw * cin + cin2; }

@@ -68,7 +68,10 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
   std::vector<BufShape> cur(P->n_bufs);
   std::vector<int64_t> buf_elems(P->n_bufs, 0);
   const int64_t n_img = 2 * (int64_t)pairs;
-  if (P->input_layout != SEMDIFF_INPUT_NHWC8) {
+  if (P->input_layout == SEMDIFF_INPUT_S2D16) {
+    if ((H | W) & 1) { set_error("the s2d stem layouts need even H and W (got %dx%d)", H, W); return SEMDIFF_ERR_ARG; }
+    cur[0] = BufShape{H / 2, W / 2, 16};
+  } else if (P->input_layout != SEMDIFF_INPUT_NHWC8) {
     if ((H | W) & 1) { set_error("the s2d stem layouts need even H and W (got %dx%d)", H, W); return SEMDIFF_ERR_ARG; }
     cur[0] = BufShape{H / 2 + (P->input_layout == SEMDIFF_INPUT_S2D_ROW4 ? 3 : 1), W / 2, 64};
   } else {
@@ -84,7 +87,7 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
       const semdiff_op& op = P->ops[i];
       const BufShape in = t[op.src];
       BufShape o = in;
-      if (op.kind == SEMDIFF_OP_CONV) o = BufShape{(in.h + 2 * op.pad - op.kh) / op.stride + 1, (in.w + 2 * op.pad - op.kw) / op.stride + 1, op.cout};
+      if (op.kind == SEMDIFF_OP_CONV) { const int ph = op.pad + (op.pad_hi < 0 ? op.pad : op.pad_hi); o = BufShape{(in.h + ph - op.kh) / op.stride + 1, (in.w + ph - op.kw) / op.stride + 1, op.cout}; }
       else if (op.kind == SEMDIFF_OP_MAXPOOL3S2) o = BufShape{(in.h - 1) / 2 + 1, (in.w - 1) / 2 + 1, in.c};
       else if (op.kind == SEMDIFF_OP_AVGPOOL) o = BufShape{in.h / op.stride, in.w / op.stride, in.c};
       t[op.dst] = o;
@@ -110,7 +113,10 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
     switch (op.kind) {
       case SEMDIFF_OP_CONV:
         if (in.c != op.cin) { set_error("op %d: cin %d != buffer channels %d", i, op.cin, in.c); return SEMDIFF_ERR_ARG; }
-        out = BufShape{(in.h + 2 * op.pad - op.kh) / op.stride + 1, (in.w + 2 * op.pad - op.kw) / op.stride + 1, op.cout};
+        {
+          const int ph = op.pad + (op.pad_hi < 0 ? op.pad : op.pad_hi);
+          out = BufShape{(in.h + ph - op.kh) / op.stride + 1, (in.w + ph - op.kw) / op.stride + 1, op.cout};
+        }
         if (op.src2 >= 0) {
           if (op.src2 >= P->n_bufs || cur[op.src2].c == 0) { set_error("op %d: bad second source buffer", i); return SEMDIFF_ERR_ARG; }
           const BufShape b2 = cur[op.src2];
@@ -161,6 +167,7 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
 
 static int choose_impl(const semdiff_plan* P, const ConvShape& cs) {
   if (P->precision == SEMDIFF_FP32 || P->conv_impl == SEMDIFF_CONV_SIMT) return SEMDIFF_CONV_SIMT;
+  if (P->conv_impl != SEMDIFF_CONV_TC_GATHER && cs.cin < 64 && conv_strip_supported(cs, P->precision)) return SEMDIFF_CONV_TC_TMA;
   if ((P->conv_impl != SEMDIFF_CONV_TC_GATHER || cs.cin2 != 0) && conv_tc_supported(cs, P->precision, true))
     return SEMDIFF_CONV_TC_TMA;
   if (conv_tc_supported(cs, P->precision, false)) return SEMDIFF_CONV_TC_GATHER;
@@ -170,7 +177,7 @@ static int choose_impl(const semdiff_plan* P, const ConvShape& cs) {
 static ConvShape conv_shape(const semdiff_op& op, const BufShape& in, const BufShape& in2, int n_img) {
   ConvShape cs;
   cs.n_img = n_img; cs.H = in.h; cs.W = in.w; cs.cin = op.cin; cs.cout = op.cout; cs.kh = op.kh; cs.kw = op.kw;
-  cs.stride = op.stride; cs.pad = op.pad; cs.relu = op.relu;
+  cs.stride = op.stride; cs.pad = op.pad; cs.relu = op.relu; cs.pad_hi = op.pad_hi;
   if (op.src2 >= 0) { cs.cin2 = op.cin2; cs.stride2 = op.stride2 < 1 ? 1 : op.stride2; cs.H2 = in2.h; cs.W2 = in2.w; }
   return cs;
 }
@@ -235,7 +242,7 @@ int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, in
                         int32_t head_ops, semdiff_plan** out) {
   if (ops == nullptr || out == nullptr || n_ops <= 0 || n_bufs < 2) { set_error("plan_create: bad arguments"); return SEMDIFF_ERR_ARG; }
   if (precision < SEMDIFF_BF16 || precision > SEMDIFF_FP32) { set_error("plan_create: bad precision %d", precision); return SEMDIFF_ERR_ARG; }
-  if (input_layout < SEMDIFF_INPUT_NHWC8 || input_layout > SEMDIFF_INPUT_S2D_ROW2) { set_error("plan_create: bad input layout %d", input_layout); return SEMDIFF_ERR_ARG; }
+  if (input_layout < SEMDIFF_INPUT_NHWC8 || input_layout > SEMDIFF_INPUT_S2D16) { set_error("plan_create: bad input layout %d", input_layout); return SEMDIFF_ERR_ARG; }
   semdiff_plan* P = new semdiff_plan();
   P->input_layout = input_layout;
   P->head_ops = head_ops < 0 || head_ops > n_ops ? 0 : head_ops;
@@ -442,12 +449,12 @@ int semdiff_pack_input(const void* gt, const void* sr, int32_t in_precision, int
 
 int semdiff_conv2d(const void* in, const void* weight, const float* bias, const void* residual, void* out, int32_t n_img,
                    int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t stride, int32_t pad,
-                   int32_t relu, const void* in2, int32_t H2, int32_t W2, int32_t cin2, int32_t stride2,
+                   int32_t relu, const void* in2, int32_t H2, int32_t W2, int32_t cin2, int32_t stride2, int32_t pad_hi,
                    int32_t precision, int32_t impl, semdiff_stream_t st_) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(st_);
   ConvShape cs;
   cs.n_img = n_img; cs.H = H; cs.W = W; cs.cin = cin; cs.cout = cout; cs.kh = kh; cs.kw = kw; cs.stride = stride;
-  cs.pad = pad; cs.relu = relu;
+  cs.pad = pad; cs.relu = relu; cs.pad_hi = pad_hi;
   if (n_img <= 0 || stride < 1 || cs.OH() <= 0 || cs.OW() <= 0) { set_error("conv2d: bad shape"); return SEMDIFF_ERR_ARG; }
   if (in2 != nullptr) {
     cs.cin2 = cin2; cs.stride2 = stride2; cs.H2 = H2; cs.W2 = W2;

@@ -51,7 +51,7 @@ class _Plan:
                 w_ptr, b_ptr = w.data_ptr(), b.data_ptr()
             arr[i] = _lib.SemdiffOp(op["kind"], op["src"], op["dst"], op["res"], op["cin"], op["cout"], op["kh"],
                                     op["kw"], op["stride"], op["pad"], op["relu"], op["tap"], op["src2"], op["cin2"],
-                                    op["stride2"], w_ptr, b_ptr)
+                                    op["stride2"], op["pad_hi"], w_ptr, b_ptr)
         handle = C.c_void_p()
         _lib.check(self.lib.semdiff_plan_create(arr, len(ops), self.program.n_bufs, self.precision,
                                                 self.program.input_layout, self.program.head_ops, C.byref(handle)),
@@ -198,16 +198,26 @@ class _B200Scorer(nn.Module):
         self._plan = {}
 
     # ---- native call -----------------------------------------------------------------------
-    def plan(self, even_size: bool = True) -> _Plan:
-        """The native plan; images with an odd height or width use a second plan whose stem is the generic
-        channel-padded conv (the space-to-depth stem layout needs even sizes)."""
-        if even_size not in self._plan:
+    def stem_variant(self, H: int = 224, W: int = 224):
+        """Which stem lowering an image size gets: "s2d16" (compact space-to-depth input + strip kernel: 16-bit modes, even
+        sizes up to 250 wide), True (row-window layout: any even size), False (odd sizes: channel-padded generic stem)."""
+        if H % 2 or W % 2:
+            return False
+        if self.family == "resnet50" and self.precision != "fp32" and W // 2 + 3 <= 128:
+            return "s2d16"
+        return True
+
+    def plan(self, stem=None) -> _Plan:
+        """The native plan for one stem variant (see stem_variant); built lazily, one per variant in use."""
+        if stem is None:
+            stem = self.stem_variant()
+        if stem not in self._plan:
             dev = next(self.w_layers.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("the module was moved off the GPU; the B200 scorer has no CPU fallback")
-            self._plan[even_size] = _Plan(self.clip, self.family, self.depth, self.precision, dev, s2d_stem=even_size,
-                                          lower_kwargs=self._lower_kwargs())
-        return self._plan[even_size]
+            self._plan[stem] = _Plan(self.clip, self.family, self.depth, self.precision, dev, s2d_stem=stem,
+                                     lower_kwargs=self._lower_kwargs())
+        return self._plan[stem]
 
     def default_microbatch(self, H: int, W: int) -> int:
         """Pairs per kernel-program pass.  Measured on B200 (profiles/): per-launch efficiency keeps improving up to
@@ -219,7 +229,7 @@ class _B200Scorer(nn.Module):
 
     def _run(self, a, b, head_w, head_b, want_grad: bool = False):
         n, _, H, W = a.shape
-        plan = self.plan(H % 2 == 0 and W % 2 == 0)
+        plan = self.plan(self.stem_variant(H, W))
         in_dt = a.dtype if a.dtype in (torch.bfloat16, torch.float16) and b.dtype == a.dtype else torch.float32
         a = a.detach().contiguous().to(in_dt)
         b = b.detach().contiguous().to(in_dt)

@@ -175,7 +175,7 @@ class Program:
             b = torch.cat([b, torch.zeros(cout_pad - b.shape[0], dtype=b.dtype)])
         op = dict(kind=_lib.OP_CONV, src=src, dst=dst, res=res, cin=w.shape[3], cout=w.shape[0],
                   kh=w.shape[1], kw=w.shape[2], stride=conv.stride[0], pad=conv.padding[0],
-                  relu=int(relu), tap=-1, src2=-1, cin2=0, stride2=1,
+                  relu=int(relu), tap=-1, src2=-1, cin2=0, stride2=1, pad_hi=-1,
                   alg_k=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1], alg_cout=conv.out_channels,
                   n_convs=1)
         w = w.reshape(w.shape[0], -1)
@@ -204,16 +204,26 @@ class Program:
                 w2[:, r, 0, base:base + 3] = w[:, ky, kx, :]
         self.input_layout = _lib.INPUT_S2D_ROW4
         self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=-1, cin=64, cout=w.shape[0], kh=4, kw=1, stride=1,
-                             pad=0, relu=1, tap=-1, src2=-1, cin2=0, stride2=1, w=w2.reshape(w2.shape[0], -1).contiguous(),
-                             b=b, alg_k=147, alg_cout=w.shape[0], n_convs=1))
+                             pad=0, relu=1, tap=-1, src2=-1, cin2=0, stride2=1, pad_hi=-1,
+                             w=w2.reshape(w2.shape[0], -1).contiguous(), b=b, alg_k=147, alg_cout=w.shape[0], n_convs=1))
+
+    def stem7_s2d16(self, conv, bn, src, dst):
+        """The same stem over the 4x smaller SEMDIFF_INPUT_S2D16 buffer ([2n, H/2, W/2, 16], channel (dy*2+dx)*3+ci):
+        a 4x4 stride-1 conv with padding 2 before / 1 after.  Same folded weights, flattened [Cout][r][j][16]; the
+        strip kernel (csrc/conv3x3_strip.cu) forms the 16 taps as shifted shared-memory views."""
+        self.stem7_s2d(conv, bn, src, dst)     # weight bytes are identical: (r, j*16 + c) == (r, j, c)
+        op = self.ops[-1]
+        op.update(cin=16, kh=4, kw=4, pad=2, pad_hi=1)
+        self.input_layout = _lib.INPUT_S2D16
+
 
     def pool(self, kind, src, dst, window):
         self.ops.append(dict(kind=kind, src=src, dst=dst, res=-1, cin=0, cout=0, kh=window, kw=window, stride=window,
-                             pad=0, relu=0, tap=-1, src2=-1, cin2=0, stride2=1, w=None, b=None))
+                             pad=0, relu=0, tap=-1, src2=-1, cin2=0, stride2=1, pad_hi=-1, w=None, b=None))
 
     def tap(self, src, j):
         self.ops.append(dict(kind=_lib.OP_TAP, src=src, dst=-1, res=-1, cin=0, cout=0, kh=0, kw=0, stride=0, pad=0,
-                             relu=0, tap=j, src2=-1, cin2=0, stride2=1, w=None, b=None))
+                             relu=0, tap=j, src2=-1, cin2=0, stride2=1, pad_hi=-1, w=None, b=None))
 
 
     def stem3_s2d(self, conv, bn, src, dst, cout_pad=64):
@@ -232,19 +242,24 @@ class Program:
         b2[:b.shape[0]] = b
         self.input_layout = _lib.INPUT_S2D_ROW2
         self.ops.append(dict(kind=_lib.OP_CONV, src=src, dst=dst, res=-1, cin=64, cout=cout, kh=2, kw=1, stride=1,
-                             pad=0, relu=1, tap=-1, src2=-1, cin2=0, stride2=1, w=w2.reshape(cout, -1).contiguous(),
+                             pad=0, relu=1, tap=-1, src2=-1, cin2=0, stride2=1, pad_hi=-1, w=w2.reshape(cout, -1).contiguous(),
                              b=b2, alg_k=27, alg_cout=w.shape[0], n_convs=1))
 
 
-def lower_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True) -> Program:
+def lower_resnet50(clip: nn.Module, depth: int, s2d_stem=True) -> Program:
     """timm resnet50; taps = layer{s}.2.act3 for s in range(4-depth, 5)  (global_eval_models.py:701).
-    s2d_stem=False keeps the stem as a channel-padded 7x7 conv (needed for odd image sizes)."""
+    s2d_stem: "s2d16" (16-bit modes, stem output width <= 125: strip kernel over the compact space-to-depth input),
+    True / "row4" (row-window layout, generic im2col path: any even size, fp32 mode), False (channel-padded 7x7 conv
+    through the gather producer: odd image sizes)."""
     P = Program()
     IN, A, B, T1, T2 = range(5)
     P.n_bufs = 5
     c1 = clip.conv1
     if s2d_stem and c1.kernel_size == (7, 7) and c1.stride == (2, 2) and c1.padding == (3, 3) and c1.in_channels == 3:
-        P.stem7_s2d(c1, clip.bn1, IN, T1)
+        if s2d_stem == "s2d16" and c1.out_channels == 64:
+            P.stem7_s2d16(c1, clip.bn1, IN, T1)
+        else:
+            P.stem7_s2d(c1, clip.bn1, IN, T1)
     else:
         P.conv(c1, clip.bn1, IN, T1, cin_pad=8)
     P.pool(_lib.OP_MAXPOOL3S2, T1, A, 3)
@@ -321,14 +336,15 @@ LOWER = {"resnet50": lower_resnet50, "resnet50_clip.openai": lower_clip_resnet50
 
 def conv_flops(program: Program, H: int, W: int) -> int:
     """Algorithmic FLOPs (2*MAC, unpadded Cin) of the conv ops for ONE HxW image."""
-    pad_rows = {_lib.INPUT_S2D_ROW4: 3, _lib.INPUT_S2D_ROW2: 1}.get(program.input_layout)
-    shapes = {0: (H // 2 + pad_rows, W // 2) if pad_rows else (H, W)}
+    pad_rows = {_lib.INPUT_S2D_ROW4: 3, _lib.INPUT_S2D_ROW2: 1, _lib.INPUT_S2D16: 0}.get(program.input_layout)
+    shapes = {0: (H // 2 + pad_rows, W // 2) if pad_rows is not None else (H, W)}
     total = 0
     for op in program.ops:
         h, w = shapes[op["src"]]
         if op["kind"] == _lib.OP_CONV:
-            oh = (h + 2 * op["pad"] - op["kh"]) // op["stride"] + 1
-            ow = (w + 2 * op["pad"] - op["kw"]) // op["stride"] + 1
+            ph = op["pad"] + (op["pad"] if op["pad_hi"] < 0 else op["pad_hi"])
+            oh = (h + ph - op["kh"]) // op["stride"] + 1
+            ow = (w + ph - op["kw"]) // op["stride"] + 1
             total += 2 * oh * ow * op["alg_cout"] * op["alg_k"]
             shapes[op["dst"]] = (oh, ow)
         elif op["kind"] == _lib.OP_MAXPOOL3S2:

@@ -28,11 +28,12 @@ def nchw(x: torch.Tensor) -> torch.Tensor:
 
 
 def conv2d(x_nhwc, w_ohwi, bias, residual, stride, pad, relu, precision: str, impl: int, x2_nhwc=None, w2=None,
-           stride2=1):
+           stride2=1, pad_hi=-1):
     """w_ohwi [Cout,KH,KW,Cin]; optional fused second source x2 [n,H2,W2,Cin2] with 1x1 weights w2 [Cout,Cin2]."""
     n, H, W, cin = x_nhwc.shape
     cout, kh, kw, _ = w_ohwi.shape
-    oh, ow = (H + 2 * pad - kh) // stride + 1, (W + 2 * pad - kw) // stride + 1
+    pa = pad if pad_hi < 0 else pad_hi
+    oh, ow = (H + pad + pa - kh) // stride + 1, (W + pad + pa - kw) // stride + 1
     # compute-sanitizer is closed on this GPU pool, so every conv test carries its own canary: the output sits between
     # two guard regions that must come back untouched (catches out-of-range TMA stores / epilogue writes)
     guard = 8192
@@ -48,7 +49,7 @@ def conv2d(x_nhwc, w_ohwi, bias, residual, stride, pad, relu, precision: str, im
     rc = lib().semdiff_conv2d(x_nhwc.data_ptr(), wmat.data_ptr(), bias.data_ptr(),
                               residual.data_ptr() if residual is not None else None, out.data_ptr(), n, H, W, cin, cout,
                               kh, kw, stride, pad, int(relu), x2_nhwc.data_ptr() if x2_nhwc is not None else None,
-                              H2, W2, cin2, stride2, _lib.PRECISIONS[precision], impl, sp())
+                              H2, W2, cin2, stride2, pad_hi, _lib.PRECISIONS[precision], impl, sp())
     _lib.check(rc, "semdiff_conv2d")
     torch.cuda.synchronize()
     assert bool((arena[:guard] == 123.0).all()) and bool((arena[guard + numel:] == 123.0).all()), "kernel wrote outside its output"

@@ -75,6 +75,26 @@ def test_conv_rowwindow_strip(geom):
     _check(out, ref, "bf16")
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("geom", [(2, 112, 112), (3, 56, 56), (1, 11, 125), (2, 7, 20)])
+def test_conv_s2d16_stem_strip(geom, precision):
+    """4x4 stride-1 conv, padding 2 before / 1 after, over 16-channel pixels (the 7x7/2 stem on SEMDIFF_INPUT_S2D16):
+    strip kernel with 32-byte rows (SWIZZLE_32B views shifted by whole pixels)."""
+    import torch
+    from helpers import DT, conv2d
+    n, H, W = geom
+    g = torch.Generator(device="cuda").manual_seed(19)
+    dt = DT[precision]
+    x = torch.randn(n, H, W, 16, device="cuda", generator=g).to(dt)
+    w = (torch.randn(64, 4, 4, 16, device="cuda", generator=g) * (2.0 / 256) ** 0.5).to(dt)
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    out = conv2d(x, w, b, None, 1, 2, True, precision, _lib.CONV_TC_TMA, pad_hi=1).double()
+    xp = torch.nn.functional.pad(x.double().permute(0, 3, 1, 2), (2, 1, 2, 1))
+    ref = torch.relu(torch.nn.functional.conv2d(xp, w.double().permute(0, 3, 1, 2), b.double())).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    _check(out, ref, precision)
+
+
 def test_conv_tc_many_tiles_persistent():
     """More tiles than SMs: exercises the persistent loop, both TMEM accumulator stages and smem ring wrap."""
     case = (8, 56, 56, 64, 256, 1, 1, 0, True)     # M = 25088 -> 196 m-tiles x 1 n-tile

@@ -150,3 +150,26 @@ def test_clip_s2d_stem_weights_reproduce_the_3x3_stride2_conv():
     assert torch.count_nonzero(got[:, 32:]) == 0
     # the padded 64-channel stem chain: conv2 / conv3 ignore the zero half
     assert prog.ops[1]["cin"] == 64 and prog.ops[1]["cout"] == 64 and prog.ops[2]["cin"] == 64 and prog.ops[2]["cout"] == 64
+
+
+def test_s2d16_stem_lowering_reproduces_the_7x7_conv():
+    """4x4 stride-1 conv (pad 2 before / 1 after) over the plain space-to-depth layout == 7x7 stride-2 pad-3 conv."""
+    torch.manual_seed(2)
+    tree = trunks.create_trunk("resnet50")
+    with torch.no_grad():
+        tree.bn1.running_mean.normal_(); tree.bn1.running_var.uniform_(0.5, 2.0); tree.bn1.bias.normal_()
+    prog = trunks.lower_resnet50(tree, 0, "s2d16")
+    assert prog.input_layout == _lib.INPUT_S2D16
+    op = prog.ops[0]
+    assert (op["kh"], op["kw"], op["cin"], op["pad"], op["pad_hi"], op["alg_k"]) == (4, 4, 16, 2, 1, 147)
+    H, W = 12, 20
+    x = torch.randn(2, 3, H, W, dtype=torch.double)
+    s2d = torch.zeros(2, 16, H // 2, W // 2, dtype=torch.double)
+    for dy in range(2):
+        for dx in range(2):
+            s2d[:, (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = x[:, :, dy::2, dx::2]
+    w = op["w"].reshape(64, 4, 4, 16).permute(0, 3, 1, 2)
+    got = torch.nn.functional.conv2d(torch.nn.functional.pad(s2d, (2, 1, 2, 1)), w, op["b"])
+    ref = tree.bn1.double().eval()(tree.conv1.double()(x))
+    assert got.shape == ref.shape and torch.allclose(got, ref, rtol=1e-10, atol=1e-10)
+    assert abs(trunks.conv_flops(prog, 224, 224) / 1e9 - 8.174272512) < 1e-9

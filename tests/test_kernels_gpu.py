@@ -48,6 +48,22 @@ def test_pack_s2d_row_window(precision):
     assert torch.equal(out, ref.to(DT[precision]))
 
 
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_pack_s2d16(precision):
+    H, W = 12, 16
+    gt = torch.randn(2, 3, H, W, device=DEV)
+    sr = torch.randn(2, 3, H, W, device=DEV)
+    out = torch.full((4, H // 2, W // 2, 16), 7.0, dtype=DT[precision], device=DEV)
+    _lib.check(lib().semdiff_pack_input(gt.data_ptr(), sr.data_ptr(), _lib.FP32, 2, H, W, out.data_ptr(), _lib.PRECISIONS[precision],
+                                        _lib.INPUT_S2D16, sp()), "pack")
+    x = torch.cat([gt, sr])
+    ref = torch.zeros(4, H // 2, W // 2, 16, device=DEV)
+    for dy in range(2):
+        for dx in range(2):
+            ref[..., (dy * 2 + dx) * 3:(dy * 2 + dx) * 3 + 3] = x[:, :, dy::2, dx::2].permute(0, 2, 3, 1)
+    assert torch.equal(out, ref.to(DT[precision]))
+
+
 @pytest.mark.parametrize("layout", [_lib.INPUT_NHWC8, _lib.INPUT_S2D_ROW4, _lib.INPUT_S2D_ROW2])
 def test_pack_16bit_inputs_equal_fp32_inputs_of_the_same_values(layout):
     """bf16 host images packed directly == the same values passed as fp32 (the pack kernel rounds to bf16 anyway)."""

@@ -270,7 +270,7 @@ def test_c_abi_error_paths():
     w = torch.zeros(64, 24, dtype=torch.bfloat16, device="cuda"); b = torch.zeros(64, device="cuda")
     o = torch.empty(1, 8, 8, 64, dtype=torch.bfloat16, device="cuda")
     rc = lib.semdiff_conv2d(x.data_ptr(), w.data_ptr(), b.data_ptr(), None, o.data_ptr(), 1, 8, 8, 24, 64, 1, 1, 1, 0, 1,
-                            None, 0, 0, 0, 1, _lib.BF16, _lib.CONV_TC_TMA, _lib.stream_ptr())
+                            None, 0, 0, 0, 1, -1, _lib.BF16, _lib.CONV_TC_TMA, _lib.stream_ptr())
     assert rc == -3 and b"unsupported shape" in lib.semdiff_last_error()
     with pytest.raises(ValueError):
         model(gt, sr[:, :, :100])

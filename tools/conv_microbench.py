@@ -13,7 +13,7 @@ def run(n, H, W, cin, cout, k, stride, pad, impl, reps=10):
     b = torch.zeros(cout, device="cuda")
     oh, ow = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     out = torch.empty(n, oh, ow, cout, device="cuda", dtype=torch.bfloat16)
-    args = (x.data_ptr(), w.data_ptr(), b.data_ptr(), None, out.data_ptr(), n, H, W, cin, cout, k, k, stride, pad, 1, None, 0, 0, 0, 1, _lib.BF16, impl)
+    args = (x.data_ptr(), w.data_ptr(), b.data_ptr(), None, out.data_ptr(), n, H, W, cin, cout, k, k, stride, pad, 1, None, 0, 0, 0, 1, -1, _lib.BF16, impl)
     for _ in range(3): _lib.check(lib().semdiff_conv2d(*args, sp()), "conv")
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True); e0.record()
     for _ in range(reps): lib().semdiff_conv2d(*args, sp())

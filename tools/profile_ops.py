@@ -56,15 +56,16 @@ def main():
             ms, cnt = plan.profile(reset=True)
             plan.set_profiling(False)
         ops = plan.program.ops
-        shapes = {0: {1: (S // 2 + 3, S // 2, 64), 2: (S // 2 + 1, S // 2, 64)}.get(plan.program.input_layout, (S, S, 8))}
+        shapes = {0: {1: (S // 2 + 3, S // 2, 64), 2: (S // 2 + 1, S // 2, 64), 3: (S // 2, S // 2, 16)}.get(plan.program.input_layout, (S, S, 8))}
         rows, tot_conv, tot_flop = [], 0.0, 0.0
         eb = 4 if args.precision == "fp32" else 2
         for i, op in enumerate(ops):
             h, w, c = shapes[op["src"]]
             t = ms[i] / args.steps
             if op["kind"] == 0:
-                oh = (h + 2 * op["pad"] - op["kh"]) // op["stride"] + 1
-                ow = (w + 2 * op["pad"] - op["kw"]) // op["stride"] + 1
+                ph = op["pad"] + (op["pad"] if op["pad_hi"] < 0 else op["pad_hi"])
+                oh = (h + ph - op["kh"]) // op["stride"] + 1
+                ow = (w + ph - op["kw"]) // op["stride"] + 1
                 shapes[op["dst"]] = (oh, ow, op["cout"])
                 fl = 2.0 * oh * ow * op["alg_cout"] * op["alg_k"] * 2 * n
                 by = (h * w * c + oh * ow * op["cout"] * (2 if op["res"] >= 0 else 1)) * eb * 2 * n
