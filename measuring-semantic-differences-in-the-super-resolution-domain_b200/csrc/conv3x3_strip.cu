@@ -224,7 +224,10 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
 
 static bool strip_is_3x3(const ConvShape& s) { return s.cin == 64 && s.kh == 3 && s.kw == 3 && s.pad == 1 && s.pad_after() == 1; }
 static bool strip_is_rowwin(const ConvShape& s) { return s.cin == 64 && s.kw == 1 && s.kh >= 2 && s.kh <= 4 && s.pad == 0 && s.pad_after() == 0; }
-static bool strip_is_s2d16(const ConvShape& s) { return s.cin == 16 && s.kh == 4 && s.kw == 4 && s.pad == 2 && s.pad_after() == 1; }
+// space-to-depth stems: 7x7/2 pad 3 -> 4x4 (pad 2 | 1), 3x3/2 pad 1 -> 2x2 (pad 1 | 0)
+static bool strip_is_s2d16(const ConvShape& s) {
+  return s.cin == 16 && ((s.kh == 4 && s.kw == 4 && s.pad == 2 && s.pad_after() == 1) || (s.kh == 2 && s.kw == 2 && s.pad == 1 && s.pad_after() == 0));
+}
 bool conv_strip_supported(const ConvShape& s, int precision) {
   return (precision == SEMDIFF_BF16 || precision == SEMDIFF_FP16) && (strip_is_3x3(s) || strip_is_rowwin(s) || strip_is_s2d16(s)) &&
          s.stride == 1 && s.cout == 64 && s.cin2 == 0 && s.OW() + s.kw - 1 <= 128 && s.W >= 6 && s.OH() >= 1 &&

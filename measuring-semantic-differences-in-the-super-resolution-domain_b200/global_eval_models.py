@@ -203,7 +203,7 @@ class _B200Scorer(nn.Module):
         sizes up to 250 wide), True (row-window layout: any even size), False (odd sizes: channel-padded generic stem)."""
         if H % 2 or W % 2:
             return False
-        if self.family == "resnet50" and self.precision != "fp32" and W // 2 + 3 <= 128:
+        if self.precision != "fp32" and W // 2 + 3 <= 128:
             return "s2d16"
         return True
 

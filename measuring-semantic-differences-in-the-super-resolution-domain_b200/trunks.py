@@ -246,6 +246,15 @@ class Program:
                              b=b2, alg_k=27, alg_cout=w.shape[0], n_convs=1))
 
 
+    def stem3_s2d16(self, conv, bn, src, dst, cout_pad=64):
+        """The CLIP 3x3/2 stem conv over SEMDIFF_INPUT_S2D16: a 2x2 stride-1 conv, padding 1 before / 0 after."""
+        self.stem3_s2d(conv, bn, src, dst, cout_pad)
+        op = self.ops[-1]
+        w = op["w"].reshape(op["cout"], 2, 64)[:, :, :32]          # slots j = 0, 1 of the row window are the real ones
+        op.update(cin=16, kh=2, kw=2, pad=1, pad_hi=0, w=w.reshape(op["cout"], -1).contiguous())
+        self.input_layout = _lib.INPUT_S2D16
+
+
 def lower_resnet50(clip: nn.Module, depth: int, s2d_stem=True) -> Program:
     """timm resnet50; taps = layer{s}.2.act3 for s in range(4-depth, 5)  (global_eval_models.py:701).
     s2d_stem: "s2d16" (16-bit modes, stem output width <= 125: strip kernel over the compact space-to-depth input),
@@ -296,7 +305,10 @@ def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True, taps
     if s2d_stem and c1.kernel_size == (3, 3) and c1.stride == (2, 2) and c1.padding == (1, 1) and c1.in_channels == 3:
         # 32-channel stem activations are carried as 64 channels (upper half exactly zero) so that every stem conv
         # runs on the TMA-im2col tensor-core path (64 channels = one 128-byte swizzle row)
-        P.stem3_s2d(c1, st.conv1.bn, IN, T1, cout_pad=64)
+        if s2d_stem == "s2d16":
+            P.stem3_s2d16(c1, st.conv1.bn, IN, T1, cout_pad=64)
+        else:
+            P.stem3_s2d(c1, st.conv1.bn, IN, T1, cout_pad=64)
         P.conv(st.conv2.conv, st.conv2.bn, T1, T2, cin_pad=64, cout_pad=64)
         P.conv(st.conv3.conv, st.conv3.bn, T2, T1, cin_pad=64)
     else:

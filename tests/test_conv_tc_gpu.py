@@ -95,6 +95,23 @@ def test_conv_s2d16_stem_strip(geom, precision):
     _check(out, ref, precision)
 
 
+@pytest.mark.parametrize("geom", [(2, 112, 112), (3, 20, 37)])
+def test_conv_s2d16_clip_stem_strip(geom):
+    """2x2 stride-1 conv, padding 1 before / 0 after, over 16-channel pixels (the CLIP 3x3/2 stem on SEMDIFF_INPUT_S2D16)."""
+    import torch
+    from helpers import conv2d
+    n, H, W = geom
+    g = torch.Generator(device="cuda").manual_seed(23)
+    x = torch.randn(n, H, W, 16, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(64, 2, 2, 16, device="cuda", generator=g) * (2.0 / 64) ** 0.5).bfloat16()
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    out = conv2d(x, w, b, None, 1, 1, True, "bf16", _lib.CONV_TC_TMA, pad_hi=0).double()
+    xp = torch.nn.functional.pad(x.double().permute(0, 3, 1, 2), (1, 0, 1, 0))
+    ref = torch.relu(torch.nn.functional.conv2d(xp, w.double().permute(0, 3, 1, 2), b.double())).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    _check(out, ref, "bf16")
+
+
 def test_conv_tc_many_tiles_persistent():
     """More tiles than SMs: exercises the persistent loop, both TMEM accumulator stages and smem ring wrap."""
     case = (8, 56, 56, 64, 256, 1, 1, 0, True)     # M = 25088 -> 196 m-tiles x 1 n-tile
