@@ -27,6 +27,12 @@ namespace semdiff {
 //   RG = 4, ROWB = 32: the same (four row groups per strip) with 16-channel pixels (SEMDIFF_INPUT_S2D16, 32-byte rows, SWIZZLE_32B, one K = 16 MMA
 //           per tap): the 7x7/2 stem as a 4x4 conv (pad 2 before / 1 after) whose 16 taps are views shifted by
 //           (r rows, j pixels) - the 4x window expansion of the row-window layouts is never materialised.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 template <int RG, int ROWB = 128> struct StripCfg {
   // P = 128 worst case; + slack for the rows that taps shifted in W read beyond the strip (not needed for KW = 1)
   static constexpr int MAX_STRIP = (RG == 1 ? 3 : RG + 3) * 128 * ROWB + ((RG == 1 || ROWB == 32) ? 1024 : 0);
@@ -42,9 +48,10 @@ template <int RG, int ROWB = 128> struct StripCfg {
 struct alignas(64) StripParams {
   CUtensorMap tmX;  // input NHWC as (C, W, H, N), box (64, P, RT + 2, 1)
   CUtensorMap tmB;  // weights [64, 576], box (64, 64)
-  CUtensorMap tmC;  // output [M, 64], box (64, W)
+  CUtensorMap tmC;  // output as (64, OW, n_img * OH), box (64, CW, 1): a partial last column block is clipped in OW
   const float* bias;
   int H, W, OH, OW, P, RT, KH, KW, pad, n_img, tiles_per_img, relu;
+  int CW, col_blocks;  // images wider than one strip are cut into column blocks of CW output pixels (then P = 128, RT = 1)
 };
 static_assert(sizeof(StripParams) <= 896, "ConvTcLaunch::params too small");
 
@@ -112,10 +119,12 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const int b = local & 1, ph = (local >> 1) & 1;
-        const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT * RG;
+        const int n = tile / p.tiles_per_img, t_in = tile - n * p.tiles_per_img;
+        const int rg = t_in / p.col_blocks, cb = t_in - rg * p.col_blocks;
+        const int oy0 = rg * p.RT * RG, ox0 = cb * p.CW;
         mbar_wait(&strip_empty[b], ph ^ 1);
         mbar_arrive_expect_tx(&strip_full[b], strip_bytes);
-        tma_load_4d(&p.tmX, &strip_full[b], strip + b * STRIP_MAX_BYTES, 0, -p.pad, oy0 - p.pad, n);  // halo: OOB -> zeros
+        tma_load_4d(&p.tmX, &strip_full[b], strip + b * STRIP_MAX_BYTES, 0, ox0 - p.pad, oy0 - p.pad, n);  // halo: OOB -> zeros
       }
     }
   } else if (warp == 1) {
@@ -159,7 +168,9 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
     int local = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int b = local & 1, ph = (local >> 1) & 1;
-      const int n = tile / p.tiles_per_img, oy0 = (tile - n * p.tiles_per_img) * p.RT * RG;
+      const int n = tile / p.tiles_per_img, t_in = tile - n * p.tiles_per_img;
+      const int rg = t_in / p.col_blocks, cb = t_in - rg * p.col_blocks;
+      const int oy0 = rg * p.RT * RG, ox0 = cb * p.CW;
       uint8_t* cbuf = smem_c + (Cfg::C_BUFS == 2 ? b : 0) * STRIP_C_BYTES;
       if (store_thread) bulk_wait_read<Cfg::C_BUFS - 1>();
       named_bar_sync(1, 256);
@@ -203,7 +214,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       named_bar_sync(1, 256);
       if (store_thread) {
         for (int oy = 0; oy < RG * p.RT; ++oy)
-          if (oy0 + oy < p.OH) tma_store_2d(&p.tmC, cbuf + oy * p.P * 128, 0, (n * p.OH + oy0 + oy) * p.OW);
+          if (oy0 + oy < p.OH) tma_store_3d(&p.tmC, cbuf + oy * p.P * 128, 0, ox0, n * p.OH + oy0 + oy);
         bulk_commit();
       }
     }
@@ -230,7 +241,7 @@ static bool strip_is_s2d16(const ConvShape& s) {
 }
 bool conv_strip_supported(const ConvShape& s, int precision) {
   return (precision == SEMDIFF_BF16 || precision == SEMDIFF_FP16) && (strip_is_3x3(s) || strip_is_rowwin(s) || strip_is_s2d16(s)) &&
-         s.stride == 1 && s.cout == 64 && s.cin2 == 0 && s.OW() + s.kw - 1 <= 128 && s.W >= 6 && s.OH() >= 1 &&
+         s.stride == 1 && s.cout == 64 && s.cin2 == 0 && s.W >= 6 && s.OH() >= 1 && s.OW() >= 1 &&
          (int64_t)s.n_img * s.H * s.W < ((int64_t)1 << 31);
 }
 
@@ -248,11 +259,26 @@ int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, i
   memset(&p, 0, sizeof(p));
   const int RG = strip_is_3x3(s) ? 1 : (strip_is_s2d16(s) ? 4 : 2);
   const int ROWB = s.cin * 2;
-  int P = 16;
-  while (P < s.OW() + s.kw - 1) P <<= 1;
+  // Strip geometry: P pixels per strip row (power of two), RT = 128 / P output rows per row group, column blocks of
+  // CW <= P - (kw - 1) output pixels.  Pick the P that wastes the fewest of the 128 "virtual" pixels per tile
+  // (ties -> the larger P: fewer, longer TMA rows).  224x224: one block per row; 1024x1024 layer1: P = 32, 9 blocks.
+  int P = 0;
+  double best = -1.0;
+  for (int cand = 128; cand >= 16; cand >>= 1) {
+    const int cw_max = cand - (s.kw - 1);
+    if (cw_max < 1) continue;
+    const int rt = 128 / cand;
+    const int64_t blocks = (s.OW() + cw_max - 1) / cw_max;
+    const int64_t tiles = blocks * ((s.OH() + rt * RG - 1) / (rt * RG));
+    const double eff = (double)s.OW() * s.OH() / ((double)tiles * 128 * RG);
+    if (eff > best + 1e-9) { best = eff; P = cand; }
+  }
+  const int cw_max = P - (s.kw - 1);
+  p.col_blocks = (s.OW() + cw_max - 1) / cw_max;
+  p.CW = (s.OW() + p.col_blocks - 1) / p.col_blocks;  // balanced blocks
   p.P = P; p.RT = 128 / P; p.H = s.H; p.W = s.W; p.OH = s.OH(); p.OW = s.OW(); p.KH = s.kh; p.KW = s.kw; p.pad = s.pad;
   p.n_img = s.n_img; p.relu = s.relu; p.bias = q.bias;
-  p.tiles_per_img = (p.OH + p.RT * RG - 1) / (p.RT * RG);
+  p.tiles_per_img = ((p.OH + p.RT * RG - 1) / (p.RT * RG)) * p.col_blocks;
   const CUtensorMapDataType dt = precision == SEMDIFF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
     const CUtensorMapSwizzle swz = ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
@@ -275,11 +301,11 @@ int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, i
     if (r != CUDA_SUCCESS) { set_error("conv_strip: weight tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {64, (cuuint64_t)s.n_img * p.OH * p.OW};
-    const cuuint64_t strides[1] = {128};
-    const cuuint32_t box[2] = {64, (cuuint32_t)p.OW};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&p.tmC, dt, 2, q.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    const cuuint64_t dims[3] = {64, (cuuint64_t)p.OW, (cuuint64_t)s.n_img * p.OH};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)p.OW * 128};
+    const cuuint32_t box[3] = {64, (cuuint32_t)p.CW, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&p.tmC, dt, 3, q.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: output tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }

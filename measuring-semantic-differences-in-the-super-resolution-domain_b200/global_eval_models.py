@@ -200,10 +200,10 @@ class _B200Scorer(nn.Module):
     # ---- native call -----------------------------------------------------------------------
     def stem_variant(self, H: int = 224, W: int = 224):
         """Which stem lowering an image size gets: "s2d16" (compact space-to-depth input + strip kernel: 16-bit modes, even
-        sizes up to 250 wide), True (row-window layout: any even size), False (odd sizes: channel-padded generic stem)."""
+        sizes), True (row-window layout + generic kernels: fp32 mode), False (odd sizes: channel-padded generic stem)."""
         if H % 2 or W % 2:
             return False
-        if self.precision != "fp32" and W // 2 + 3 <= 128:
+        if self.precision != "fp32":
             return "s2d16"
         return True
 

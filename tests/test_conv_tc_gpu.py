@@ -48,7 +48,9 @@ STRIP_CASES = [
     (5, 14, 14, 64, 64, 3, 1, 1, False),     # P = 16, 8 rows per tile (14 = 8 + 6: ragged)
     (2, 112, 112, 64, 64, 3, 1, 1, False),   # P = 128, 1 row per tile (CLIP stem geometry)
     (2, 37, 50, 64, 64, 3, 1, 1, False),     # H odd (ragged last row group), W not a power of two
-    (1, 6, 126, 64, 64, 3, 1, 1, False),     # W + 2 == 128: the widest row the strip holds
+    (1, 6, 126, 64, 64, 3, 1, 1, False),     # W + 2 == 128: the widest row one strip holds
+    (2, 9, 256, 64, 64, 3, 1, 1, False),     # wider: 3 column blocks of 126 (last one partial), 1024x1024 layer1 geometry
+    (1, 5, 127, 64, 64, 3, 1, 1, False),     # 2 column blocks, the second a single pixel wide
 ]
 
 
@@ -76,7 +78,7 @@ def test_conv_rowwindow_strip(geom):
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
-@pytest.mark.parametrize("geom", [(2, 112, 112), (3, 56, 56), (1, 11, 125), (2, 7, 20)])
+@pytest.mark.parametrize("geom", [(2, 112, 112), (3, 56, 56), (1, 11, 125), (2, 7, 20), (1, 6, 512), (2, 5, 126)])
 def test_conv_s2d16_stem_strip(geom, precision):
     """4x4 stride-1 conv, padding 2 before / 1 after, over 16-channel pixels (the 7x7/2 stem on SEMDIFF_INPUT_S2D16):
     strip kernel with 32-byte rows (SWIZZLE_32B views shifted by whole pixels)."""
