@@ -40,27 +40,37 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs."""
+    """Samples SM clock and throttle reasons of one GPU through NVML while the timed region runs.  NVML is
+    initialised in the constructor (it takes ~100 ms) so that sampling covers the timed region from its start."""
+
+    NAMES = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz, self._halt = index, [], set(), None, threading.Event()
-
-    def run(self):
+        self.samples, self.reasons, self.max_mhz, self._halt = [], set(), None, threading.Event()
+        self._nv = self._h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
-                     0x80: "hw_power_brake_slowdown"}
-            while not self._halt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                self.reasons |= {n for bit, n in names.items() if r & bit}
-                time.sleep(0.02)
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
         except Exception as e:  # noqa: BLE001
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def run(self):
+        if self._nv is None:
+            return
+        nv = self._nv
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.reasons |= {n for bit, n in self.NAMES.items() if r & bit}
+            except Exception as e:  # noqa: BLE001
+                self.reasons.add(f"nvml_error:{type(e).__name__}")
+                return
+            time.sleep(0.005)
 
     def stop(self):
         self._halt.set()
@@ -199,10 +209,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         scores = step()
     barrier()
-    sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
