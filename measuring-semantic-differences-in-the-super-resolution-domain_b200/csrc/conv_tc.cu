@@ -596,6 +596,7 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
 }
 
 int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t st) {
+  if (L->a_mode > 200) return conv_chain_launch(L, st);
   if (L->a_mode > 100) return conv_strip_launch(L, st);
   const ConvTcParams& p = *reinterpret_cast<const ConvTcParams*>(L->params);
   if (L->precision == SEMDIFF_BF16) return launch_mode<__nv_bfloat16>(p, L->block_n, L->a_mode, st);

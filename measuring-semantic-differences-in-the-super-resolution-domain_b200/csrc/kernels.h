@@ -42,7 +42,7 @@ int launch_conv_tc(const ConvPtrs& ptr, const ConvShape& s, int precision, bool 
 bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma);
 // prepared launch (TMA descriptors encoded once, reused while pointers and shapes stay the same)
 struct alignas(64) ConvTcLaunch {
-  unsigned char params[896];
+  unsigned char params[1280];
   int block_n, a_mode, precision;
 };
 int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& ptr, const ConvShape& s, int precision, bool use_tma);
@@ -51,6 +51,13 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t stream);
 bool conv_strip_supported(const ConvShape& s, int precision);
 int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& ptr, const ConvShape& s, int precision);
 int conv_strip_launch(const ConvTcLaunch* L, cudaStream_t stream);
+
+// conv1x1 (-> 256 channels, residual or fused shortcut) chained with the next conv1x1 (256 -> 64 | 128): the 256-channel
+// tile is written out AND consumed from shared memory by the second GEMM (conv_chain.cu); conv_tc_launch dispatches to it
+bool conv_chain_supported(const ConvShape& s1, const ConvShape& s2, bool has_res, int precision);
+int conv_chain_prepare(ConvTcLaunch* L, const ConvPtrs& ptr1, const ConvShape& s1, const ConvPtrs& ptr2, const ConvShape& s2,
+                       int precision);
+int conv_chain_launch(const ConvTcLaunch* L, cudaStream_t stream);
 
 int distance_parts(int hw, int c);
 int launch_distance(const void* act, int n_pairs, int hw, int c, const float* w, int normalize, float* partial,

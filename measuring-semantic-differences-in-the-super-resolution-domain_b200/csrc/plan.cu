@@ -31,6 +31,7 @@ struct ShapePlan {
   std::vector<ConvTcLaunch> tc;                // per op (valid where impl is a tcgen05 one)
   std::vector<ConvTcLaunch> tc_tail;           // head ops only: launch for the ragged last chunk
   std::vector<int> impl;                       // per op: SEMDIFF_CONV_*
+  std::vector<char> fused_away;                // per op: 1 = computed by the chained launch of an earlier op (conv_chain.cu)
   int chunk_imgs = 0;                          // images per head chunk (0 = head ops run on the whole micro-batch)
   int64_t partial_offset = 0;
   int64_t total_bytes = 0;
@@ -196,15 +197,35 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
   S->tc.resize(n_ops);
   S->tc_tail.resize(n_ops);
   S->impl.assign(n_ops, 0);
+  S->fused_away.assign(n_ops, 0);
+  // SEMDIFF_NO_CHAIN=1 keeps every conv in its own launch (A/B testing)
+  static const bool chain_ok = getenv("SEMDIFF_NO_CHAIN") == nullptr;
   const int chunk = S->chunk_imgs, tail = chunk > 0 ? (2 * pairs) % chunk : 0;
   for (int i = 0; i < n_ops; ++i) {
     const semdiff_op& op = P->ops[i];
-    if (op.kind != SEMDIFF_OP_CONV) continue;
+    if (op.kind != SEMDIFF_OP_CONV || S->fused_away[i]) continue;
     const bool in_head = chunk > 0 && i < P->head_ops;
     if (in_head && i + 1 == P->head_ops) { set_error("the last head op must be a pooling op"); return SEMDIFF_ERR_UNSUPPORTED; }
     const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], in_head ? chunk : 2 * pairs);
     const int impl = choose_impl(P, cs);
     S->impl[i] = impl;
+    if (impl == SEMDIFF_CONV_TC_TMA && chain_ok && P->conv_impl == SEMDIFF_CONV_AUTO && !in_head) {
+      // block boundary in the 256-channel stage: this conv's output tile feeds the next block's first 1x1 conv from
+      // shared memory (TAP ops in between only read the output, which is still written in full)
+      int j = i + 1;
+      while (j < n_ops && P->ops[j].kind == SEMDIFF_OP_TAP) ++j;
+      if (j < n_ops && P->ops[j].kind == SEMDIFF_OP_CONV && P->ops[j].src == op.dst && P->ops[j].res < 0 && P->ops[j].src2 < 0 &&
+          P->ops[j].dst != op.src && P->ops[j].dst != op.res && P->ops[j].dst != op.src2 && P->ops[j].dst != op.dst) {
+        const ConvShape c2 = conv_shape(P->ops[j], S->op_src[j], S->op_src2[j], 2 * pairs);
+        if (conv_chain_supported(cs, c2, op.res >= 0, P->precision)) {
+          int rc = conv_chain_prepare(&S->tc[i], conv_ptrs(op, *S, ws), cs, conv_ptrs(P->ops[j], *S, ws), c2, P->precision);
+          if (rc != 0) return rc;
+          S->impl[j] = SEMDIFF_CONV_TC_TMA;
+          S->fused_away[j] = 1;
+          continue;
+        }
+      }
+    }
     if (impl == SEMDIFF_CONV_TC_TMA || impl == SEMDIFF_CONV_TC_GATHER) {
       int rc = conv_tc_prepare(&S->tc[i], conv_ptrs(op, *S, ws), cs, P->precision, impl == SEMDIFF_CONV_TC_TMA);
       if (rc != 0) return rc;
@@ -373,6 +394,7 @@ int semdiff_score(semdiff_plan* P, const void* gt, const void* sr, int32_t in_pr
       const BufShape in = S.op_src[i];
       char* src = ws + S.buf_offset[op.src];
       int rc = 0;
+      if (S.fused_away[i]) return 0;
       if (op.kind == SEMDIFF_OP_TAP) {
         ProfScope ps(P, n_ops + 1, st);
         const int j = op.tap, hw = in.h * in.w;
@@ -476,6 +498,26 @@ int semdiff_conv2d(const void* in, const void* weight, const float* bias, const 
   }
   set_error("conv2d: bad impl %d", impl);
   return SEMDIFF_ERR_ARG;
+}
+
+int semdiff_conv1x1_chain(const void* in, const void* in2, const void* w1, const float* bias1, const void* residual, void* out1,
+                          const void* w2, const float* bias2, void* out2, int64_t m, int32_t cin, int32_t cin2, int32_t cout2,
+                          int32_t relu1, int32_t relu2, int32_t precision, semdiff_stream_t st_) {
+  if (in == nullptr || w1 == nullptr || bias1 == nullptr || out1 == nullptr || w2 == nullptr || bias2 == nullptr || out2 == nullptr ||
+      m <= 0 || m >= ((int64_t)1 << 31) || cin <= 0 || cin2 < 0 || (in2 == nullptr) != (cin2 == 0)) {
+    set_error("conv1x1_chain: bad arguments");
+    return SEMDIFF_ERR_ARG;
+  }
+  ConvShape s1;  // the pixel dimension is carried as one image of m x 1 pixels
+  s1.n_img = 1; s1.H = (int)m; s1.W = 1; s1.cin = cin; s1.cout = 256; s1.kh = s1.kw = 1; s1.stride = 1; s1.pad = 0; s1.relu = relu1;
+  if (in2 != nullptr) { s1.cin2 = cin2; s1.stride2 = 1; s1.H2 = (int)m; s1.W2 = 1; }
+  ConvShape s2 = s1;
+  s2.cin = 256; s2.cin2 = 0; s2.cout = cout2; s2.relu = relu2;
+  ConvTcLaunch L;
+  int rc = conv_chain_prepare(&L, ConvPtrs{in, in2, w1, bias1, residual, out1}, s1, ConvPtrs{out1, nullptr, w2, bias2, nullptr, out2}, s2,
+                              precision);
+  if (rc != 0) return rc;
+  return conv_chain_launch(&L, reinterpret_cast<cudaStream_t>(st_));
 }
 
 int semdiff_maxpool3x3s2(const void* in, void* out, int32_t n, int32_t H, int32_t W, int32_t c, int32_t precision,

@@ -94,6 +94,24 @@ def test_tc_path_equals_simt_path_bf16():
     assert rel_err(gather, simt) < 5e-3
 
 
+@pytest.mark.parametrize("trunk", ["resnet50", "resnet50_clip.openai"])
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+def test_chained_block_boundaries_bit_exact(trunk, precision):
+    """The plan fuses conv3 -> next conv1 across the 256-channel block boundaries (csrc/conv_chain.cu); an explicit conv
+    impl keeps one launch per conv.  Same rounded tile either way, so scores and launch counts differ by the fusion only."""
+    oracle, model = oracle_and_module(trunk, 3, precision)
+    gt, sr = make_pairs(6, seed=11)
+    with torch.no_grad():
+        fused = model(gt.cuda(), sr.cuda()).cpu()
+        n_fused = model.plan().last_launches()
+        model.plan().set_conv_impl(semdiff_b200._lib.CONV_TC_TMA)
+        plain = model(gt.cuda(), sr.cuda()).cpu()
+        n_plain = model.plan().last_launches()
+    print(f"[chain] {trunk} {precision}: {n_plain} -> {n_fused} launches")
+    assert n_plain - n_fused == 3
+    assert torch.equal(fused, plain)
+
+
 def test_goldens_fp32():
     with open(GOLDEN) as f:
         records = json.load(f)["records"]
