@@ -108,6 +108,11 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
     if (ns < 256) ns <<= 1;
   }
 }
+// for waits that are short by design (a prefetched tile, an accumulator one phase ahead): a bounded 32 ns nap keeps the
+// issue slots free without overshooting the wake-up by a large fraction of the phase
+__device__ __forceinline__ void mbar_wait_short(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(32);
+}
 
 // ---------------------------------------------------------------------------------------------
 // proxy fences, cp.async (LDGSTS)

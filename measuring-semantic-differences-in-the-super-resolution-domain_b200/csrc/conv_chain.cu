@@ -11,9 +11,11 @@
 // Reference: the timm bottleneck the scorer runs under /root/reference/models/global_eval_models.py:364,371.
 //
 // Roles (352 threads): warp 0 TMA producer (x tiles; W1 / W2 once per CTA, resident), warp 1 tcgen05 issuer
-// (GEMM1 per 128-column chunk into 2 TMEM stages, GEMM2 one chunk behind into 2 more), warps 2-9 epilogue,
-// warp 10 residual loader.  C ring slots cycle  chunk0, chunk1, t-tile  per pixel tile; a slot is reusable when the
-// TMA store has read it AND (for the y chunks) GEMM2 has consumed it.
+// (GEMM1 per 128-column chunk into 2 TMEM stages, GEMM2 one chunk behind into 2 more), warps 2-9 epilogue
+// (TMEM -> +bias (+residual, in place) -> ReLU -> 16-bit staged tile; no barrier between the warps), warp 10 C-ring I/O
+// (TMA store of each staged slot, residual prefetch into it as soon as the store has read it).  C ring slots cycle
+// chunk0, chunk1, t-tile  per pixel tile; a slot is reusable when the TMA store has read it AND (for the y chunks)
+// GEMM2 has consumed it.
 #include <cuda.h>
 #include <stdlib.h>
 #include <string.h>
@@ -30,7 +32,7 @@ constexpr int W1_BLOCK = CHUNK * 64 * 2;        // [128 output channels][64 k]
 constexpr int SLOT = BLOCK_M * CHUNK * 2;       // one staged chunk: 2 boxes of [128 px][64 ch]
 constexpr int BOX = BLOCK_M * 64 * 2;
 constexpr int MAX_STAGES = 6, MAX_RING = 4, EPI_WARPS = 8, THREADS = (2 + EPI_WARPS + 1) * 32;
-constexpr int NUM_BARS = 2 * MAX_STAGES + 8 + 3 * MAX_RING + 1;
+constexpr int NUM_BARS = 2 * MAX_STAGES + 8 + 4 * MAX_RING + 1;
 constexpr int SMEM_LIMIT = 232448;
 }  // namespace chain
 
@@ -61,7 +63,8 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
   uint64_t* res_full = t2_empty + 2;
   uint64_t* c_free = res_full + MAX_RING;
   uint64_t* c_ready = c_free + MAX_RING;
-  uint64_t* w_bar = c_ready + MAX_RING;
+  uint64_t* staged = c_ready + MAX_RING;
+  uint64_t* w_bar = staged + MAX_RING;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -81,7 +84,10 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
       mbar_init(&t1_full[i], 1); mbar_init(&t1_empty[i], EPI_WARPS);
       mbar_init(&t2_full[i], 1); mbar_init(&t2_empty[i], EPI_WARPS);
     }
-    for (int i = 0; i < MAX_RING; ++i) { mbar_init(&res_full[i], 1); mbar_init(&c_free[i], 2); mbar_init(&c_ready[i], 1); }
+    for (int i = 0; i < MAX_RING; ++i) {
+      mbar_init(&res_full[i], 1); mbar_init(&c_free[i], 1);
+      mbar_init(&c_ready[i], EPI_WARPS); mbar_init(&staged[i], EPI_WARPS);
+    }
     mbar_init(w_bar, 1);
     mbar_fence_init();
   }
@@ -171,8 +177,8 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
         if (prev_slot >= 0) gemm2(prev_slot, prev_g, prev_local);
         prev_slot = slot; prev_g = g; prev_local = local;
         if (++slot == R) slot = 0;
+        if (g == 0 && local > 0 && ++slot == R) slot = 0;  // the slot of t(i - 1), staged between the two y chunks
       }
-      if (++slot == R) slot = 0;  // the t tile's slot
     }
     if (prev_slot >= 0) gemm2(prev_slot, prev_g, prev_local);
   } else if (warp < 2 + EPI_WARPS) {
@@ -180,9 +186,7 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
-    const bool store_thread = (warp == 2 && leader);
-    int slot = 0, sphase = 0, c = 0, local = 0, prev_slot = -1;
-    bool prev_is_t = false;
+    int slot = 0, sphase = 0, c = 0, local = 0;
     // bias + (residual) + relu + 16-bit pack of 32 accumulator columns into the swizzled staging rows
     auto emit = [&](const uint32_t (&v)[32], const float* bias, uint32_t row_addr, int j0, bool add_res, bool relu) {
 #pragma unroll
@@ -210,96 +214,126 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
         asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
       }
     };
-    // store-thread bookkeeping after a slot's stores were issued: every older store has read its slot -> free it
-    auto retire = [&](int cur_slot, bool cur_is_t) {
-      bulk_commit();
-      bulk_wait_read<1>();
-      if (prev_slot >= 0) {
-        mbar_arrive(&c_free[prev_slot]);
-        if (prev_is_t) mbar_arrive(&c_free[prev_slot]);   // no GEMM2 reads the t tile: the store is its only consumer
+    // this warp's part of the slot is staged: visible to the async proxy (TMA store, GEMM2), then signal - the epilogue
+    // warps never synchronise with each other
+    auto publish = [&](int s, bool is_y) {
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&staged[s]);
+        if (is_y) mbar_arrive(&c_ready[s]);
       }
-      prev_slot = cur_slot;
-      prev_is_t = cur_is_t;
+    };
+    // phase order per pixel tile i:  y chunk 0 of i,  t of i - 1,  y chunk 1 of i  - GEMM2 of tile i - 1 retires while
+    // chunk 0 of tile i is in the epilogue, so the t phase never waits for the tensor pipe
+    auto y_phase = [&](int tile, int g) {
+      uint8_t* cbuf = smem_c + slot * SLOT;
+      const int acc = c & 1;
+      mbar_wait_short(&res_full[slot], sphase);
+      mbar_wait_short(&t1_full[acc], (c >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int u = half; u < CHUNK / 32; u += 2) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * CHUNK + u * 32, v);
+        tmem_ld_wait();
+        if (u + 2 >= CHUNK / 32) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t1_empty[acc]);
+        }
+        emit(v, p.bias1 + g * CHUNK + u * 32, smem_u32(cbuf + (u >> 1) * BOX) + row * 128, (u & 1) * 4, p.has_res != 0, p.relu1 != 0);
+      }
+      publish(slot, true);
+      ++c;
+      if (++slot == R) { slot = 0; sphase ^= 1; }
+    };
+    auto t_phase = [&](int tl) {   // tl: CTA-local index of the pixel tile
+      uint8_t* cbuf = smem_c + slot * SLOT;
+      const int a2 = tl & 1;
+      mbar_wait_short(&res_full[slot], sphase);
+      mbar_wait_short(&t2_full[a2], (tl >> 1) & 1);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int u = half; u < N2 / 32; u += 2) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_acc2 + lane_addr + a2 * N2 + u * 32, v);
+        tmem_ld_wait();
+        if (u + 2 >= N2 / 32) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t2_empty[a2]);
+        }
+        emit(v, p.bias2 + u * 32, smem_u32(cbuf + (u >> 1) * BOX) + row * 128, (u & 1) * 4, false, p.relu2 != 0);
+      }
+      publish(slot, false);
+      if (++slot == R) { slot = 0; sphase ^= 1; }
     };
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++local) {
-#pragma unroll 1
-      for (int g = 0; g < G; ++g, ++c) {
-        uint8_t* cbuf = smem_c + slot * SLOT;
-        const int acc = c & 1;
-        mbar_wait_backoff(&res_full[slot], sphase);
-        mbar_wait_backoff(&t1_full[acc], (c >> 1) & 1);
-        tcgen05_fence_after();
-#pragma unroll 1
-        for (int u = half; u < CHUNK / 32; u += 2) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + lane_addr + acc * CHUNK + u * 32, v);
-          tmem_ld_wait();
-          if (u + 2 >= CHUNK / 32) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t1_empty[acc]);
-          }
-          emit(v, p.bias1 + g * CHUNK + u * 32, smem_u32(cbuf + (u >> 1) * BOX) + row * 128, (u & 1) * 4, p.has_res != 0, p.relu1 != 0);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, EPI_WARPS * 32);
-        if (store_thread) {
-          mbar_arrive(&c_ready[slot]);   // GEMM2 may read the staged chunk
-#pragma unroll
-          for (int b = 0; b < CHUNK / 64; ++b) tma_store_2d(&p.tmC, cbuf + b * BOX, g * CHUNK + b * 64, tile * BLOCK_M);
-          retire(slot, false);
-        }
-        if (++slot == R) { slot = 0; sphase ^= 1; }
-      }
-      {
-        // t tile: second GEMM's accumulator -> bias2, relu2 -> staged -> TMA store
-        uint8_t* cbuf = smem_c + slot * SLOT;
-        const int a2 = local & 1;
-        mbar_wait_backoff(&res_full[slot], sphase);
-        mbar_wait_backoff(&t2_full[a2], (local >> 1) & 1);
-        tcgen05_fence_after();
-#pragma unroll 1
-        for (int u = half; u < N2 / 32; u += 2) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_acc2 + lane_addr + a2 * N2 + u * 32, v);
-          tmem_ld_wait();
-          if (u + 2 >= N2 / 32) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&t2_empty[a2]);
-          }
-          emit(v, p.bias2 + u * 32, smem_u32(cbuf + (u >> 1) * BOX) + row * 128, (u & 1) * 4, false, p.relu2 != 0);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1, EPI_WARPS * 32);
-        if (store_thread) {
-#pragma unroll
-          for (int b = 0; b < N2 / 64; ++b) tma_store_2d(&p.tmC2, cbuf + b * BOX, b * 64, tile * BLOCK_M);
-          retire(slot, true);
-        }
-        if (++slot == R) { slot = 0; sphase ^= 1; }
-      }
+      y_phase(tile, 0);
+      if (local > 0) t_phase(local - 1);
+      y_phase(tile, 1);
     }
-    if (store_thread) bulk_wait<0>();
+    if (local > 0) t_phase(local - 1);
   } else {
-    // ===================== residual loader / slot granter =====================
-    if (leader) {
-      int slot = 0, sphase = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-        for (int g = 0; g <= G; ++g) {
-          mbar_wait(&c_free[slot], sphase ^ 1);
-          if (g < G && p.has_res) {
-            mbar_arrive_expect_tx(&res_full[slot], SLOT);
-            uint8_t* cbuf = smem_c + slot * SLOT;
+    // ===================== C-ring I/O: TMA stores of staged slots, then residual prefetch into the freed slot ==========
+    // One thread owns both directions, so a slot is handed back as soon as its store has READ it (plus, for y chunks,
+    // GEMM2's commit) and the residual of the phase R ahead starts loading at once: R - 1 phases of HBM latency hidden.
+    if (leader && blockIdx.x < p.m_tiles) {
+      const int n_local = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+      const int total = (G + 1) * n_local;
+      // cursor over the phase order: sub 0 = y chunk 0 of tile i, 1 = t of tile i - 1, 2 = y chunk 1 of tile i
+      struct Cursor {
+        int i = 0, sub = 0;
+        __device__ bool is_y() const { return sub != 1; }
+        __device__ int g() const { return sub >> 1; }
+        __device__ int local() const { return sub == 1 ? i - 1 : i; }
+        __device__ void next(int n) {
+          if (sub == 0) sub = i > 0 ? 1 : 2;
+          else if (sub == 1) sub = 2;
+          else { ++i; sub = i < n ? 0 : 1; }
+        }
+      } ld, stc;
+      int k_load = 0, l_slot = 0, k_store = 0, s_slot = 0, s_phase = 0;
+      uint32_t free_phase = 0, last_y = 0;
+      while (k_store < total) {
+        while (k_load < total && k_load < k_store + R) {
+          if ((last_y >> l_slot) & 1) {   // previous tenant was a y chunk: GEMM2 must have consumed it
+            mbar_wait(&c_free[l_slot], (free_phase >> l_slot) & 1);
+            free_phase ^= 1u << l_slot;
+          }
+          last_y = (last_y & ~(1u << l_slot)) | ((ld.is_y() ? 1u : 0u) << l_slot);
+          if (ld.is_y() && p.has_res) {
+            const int row0 = ((int)blockIdx.x + ld.local() * (int)gridDim.x) * BLOCK_M;
+            mbar_arrive_expect_tx(&res_full[l_slot], SLOT);
+            uint8_t* cbuf = smem_c + l_slot * SLOT;
 #pragma unroll
             for (int b = 0; b < CHUNK / 64; ++b)
-              tma_load_2d(&p.tmR, &res_full[slot], cbuf + b * BOX, g * CHUNK + b * 64, tile * BLOCK_M);
+              tma_load_2d(&p.tmR, &res_full[l_slot], cbuf + b * BOX, ld.g() * CHUNK + b * 64, row0);
           } else {
-            mbar_arrive(&res_full[slot]);
+            mbar_arrive(&res_full[l_slot]);
           }
-          if (++slot == R) { slot = 0; sphase ^= 1; }
+          ++k_load;
+          ld.next(n_local);
+          if (++l_slot == R) l_slot = 0;
         }
+        mbar_wait(&staged[s_slot], s_phase);
+        uint8_t* cbuf = smem_c + s_slot * SLOT;
+        const int row0 = ((int)blockIdx.x + stc.local() * (int)gridDim.x) * BLOCK_M;
+        if (stc.is_y()) {
+#pragma unroll
+          for (int b = 0; b < CHUNK / 64; ++b) tma_store_2d(&p.tmC, cbuf + b * BOX, stc.g() * CHUNK + b * 64, row0);
+        } else {
+#pragma unroll
+          for (int b = 0; b < N2 / 64; ++b) tma_store_2d(&p.tmC2, cbuf + b * BOX, b * 64, row0);
+        }
+        bulk_commit();
+        bulk_wait_read<0>();
+        ++k_store;
+        stc.next(n_local);
+        if (++s_slot == R) { s_slot = 0; s_phase ^= 1; }
       }
+      bulk_wait<0>();  // smem must stay valid until the last store has completed
     }
   }
 
@@ -374,7 +408,9 @@ int conv_chain_prepare(ConvTcLaunch* L, const ConvPtrs& q1, const ConvShape& s1,
   // shared-memory split: resident W1 / W2, then the C ring (residual prefetch depth), the rest to the x ring
   const int fixed = G * p.nkb1 * W1_BLOCK + (N1 / 64) * p.n2 * 128;
   const int avail = SMEM_LIMIT - 1024 - NUM_BARS * 8 - 16 - fixed;
-  int ring = p.has_res ? 3 : 2;
+  // measured on B200 (profiles/r1_chain_conv.md): with a residual, 4 slots (3 residual tiles in flight) reach the HBM
+  // roofline where 3 lose 13 %; without one the ring only buffers stores
+  int ring = p.has_res ? MAX_RING : 2;
   if (const char* e = getenv("SEMDIFF_CHAIN_RING")) { const int v = atoi(e); if (v >= 2 && v <= MAX_RING) ring = v; }
   int stages = (avail - ring * SLOT) / A_STAGE;
   while (stages < 2 * p.nkb1 && ring > 2) { --ring; stages = (avail - ring * SLOT) / A_STAGE; }
