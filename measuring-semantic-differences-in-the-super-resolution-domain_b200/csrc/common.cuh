@@ -234,6 +234,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t fmt_ab, uint32_t 
   return (1u << 4) | (fmt_ab << 7) | (fmt_ab << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// Programmatic dependent launch (opt-in, SEMDIFF_PDL=1: the trunk kernels are then launched with programmatic stream
+// serialization, kernels.h launch_pdl): pdl_trigger lets the NEXT kernel's CTAs start their prologue (barrier init, TMEM allocation, resident
+// weights) on SMs this grid has already vacated; pdl_wait blocks until the PREVIOUS grid has completed and its writes
+// are visible - it must precede (directly, or through an mbarrier chain) every access to activations.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(

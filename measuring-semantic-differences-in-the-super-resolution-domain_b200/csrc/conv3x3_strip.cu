@@ -111,11 +111,13 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_trigger();
 
   if (warp == 0) {
     if (leader) {
       mbar_arrive_expect_tx(b_bar, taps * Cfg::B_TAP_BYTES);
       for (int t = 0; t < taps; ++t) tma_load_2d(&p.tmB, b_bar, smem_b + t * Cfg::B_TAP_BYTES, t * (ROWB / 2), 0);
+      pdl_wait();  // the strips are the previous kernel's output
       int local = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
         const int b = local & 1, ph = (local >> 1) & 1;
@@ -322,8 +324,7 @@ static int strip_launch_t(const StripParams& p, int dev, int sms, cudaStream_t s
     configured[dev] = true;
   }
   const int tiles = p.n_img * p.tiles_per_img;
-  kern<<<tiles < sms ? tiles : sms, 320, StripCfg<RG, ROWB>::SMEM, st>>>(p);
-  SEMDIFF_CUDA_OK(cudaGetLastError());
+  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(320), StripCfg<RG, ROWB>::SMEM, st, p));
   return 0;
 }
 

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_acc2 = tmem_base + 2 * CHUNK;
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
         for (int kb = 0; kb < p.nkb1; ++kb)
           tma_load_2d(&p.tmW1, w_bar, smem_w1 + (g * p.nkb1 + kb) * W1_BLOCK, kb * 64, g * CHUNK);
       for (int kb = 0; kb < N1 / 64; ++kb) tma_load_2d(&p.tmW2, w_bar, smem_w2 + kb * W2_BLOCK, kb * 64, 0);
+      pdl_wait();  // x tiles are the previous kernel's output
       int stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
         for (int kb = 0; kb < p.nkb1; ++kb) {
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
     // One thread owns both directions, so a slot is handed back as soon as its store has READ it (plus, for y chunks,
     // GEMM2's commit) and the residual of the phase R ahead starts loading at once: R - 1 phases of HBM latency hidden.
     if (leader && blockIdx.x < p.m_tiles) {
+      pdl_wait();
       const int n_local = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = (G + 1) * n_local;
       // cursor over the phase order: sub 0 = y chunk 0 of tile i, 1 = t of tile i - 1, 2 = y chunk 1 of tile i
@@ -442,8 +445,7 @@ static int chain_launch_t(const ChainParams& p, cudaStream_t st) {
     SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, chain::SMEM_LIMIT));
     configured[dev] = chain::SMEM_LIMIT;
   }
-  kern<<<p.m_tiles < sms ? p.m_tiles : sms, chain::THREADS, p.smem_bytes, st>>>(p);
-  SEMDIFF_CUDA_OK(cudaGetLastError());
+  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(p.m_tiles < sms ? p.m_tiles : sms), dim3(chain::THREADS), (size_t)p.smem_bytes, st, p));
   return 0;
 }
 

@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_trigger();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -146,6 +147,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
         for (int kb = 0; kb < p.num_kb; ++kb)
           tma_load_2d(&p.tmB, bres_bar, smem_b + kb * Cfg::B_STAGE_BYTES, kb * BLOCK_K, 0);
       }
+      pdl_wait();  // activations of the previous kernel (everything downstream of these loads is ordered by mbarriers)
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int n = 0, h0 = 0, w0 = 0, h2 = 0, w2 = 0;
@@ -301,6 +303,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
   } else if (warp == (kAMode == A_GATHER ? 10 : 2 + EPI_WARPS)) {
     // ===================== residual loader =====================
     if (leader && p.has_res) {
+      pdl_wait();
       int gc = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
@@ -324,6 +327,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const uint32_t row_off = row * 128, sw = row & 7;
     int stage = 0, phase = 0, arr_stage = 0;
     int issued = 0;
+    pdl_wait();
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles;
       const int gm = m_tile * BLOCK_M + row;
@@ -515,8 +519,7 @@ static int launch_t(const ConvTcParams& p, cudaStream_t st) {
   }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, cta_threads<BLOCK_N, kAMode>(), Cfg::SMEM_BYTES, st>>>(p);
-  SEMDIFF_CUDA_OK(cudaGetLastError());
+  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(cta_threads<BLOCK_N, kAMode>()), Cfg::SMEM_BYTES, st, p));
   return 0;
 }
 

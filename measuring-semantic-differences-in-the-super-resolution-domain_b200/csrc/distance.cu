@@ -51,6 +51,8 @@ template <typename T, bool kRegW>
 __global__ void __launch_bounds__(DIST_THREADS) distance_kernel(const T* __restrict__ act, int n_pairs, int64_t elems,
                                                                 int C, const float* __restrict__ w,
                                                                 int64_t chunks_per_part, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   __shared__ float red[DIST_THREADS / 32];
   const int pair = blockIdx.y, part = blockIdx.x;
   const T* a = act + (int64_t)pair * elems;
@@ -110,6 +112,8 @@ template <typename T>
 __global__ void __launch_bounds__(DIST_THREADS) distance_norm_kernel(const T* __restrict__ act, int n_pairs, int hw,
                                                                      int C, const float* __restrict__ w,
                                                                      int pix_per_part, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   __shared__ float red[DIST_THREADS / 32];
   const int pair = blockIdx.y, part = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(DIST_THREADS) distance_norm_kernel(const T* __
 template <typename T>
 __global__ void __launch_bounds__(128) chan_mean_kernel(const T* __restrict__ act, int n_pairs, int hw, int C,
                                                         float* __restrict__ chan_mean, int chan_stride) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   const int pair = blockIdx.y;
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   if (c8 * 8 >= C) return;
@@ -184,19 +190,19 @@ static int distance_t(const void* act, int n_pairs, int hw, int c, const float* 
   dim3 grid(parts, n_pairs);
   if (normalize) {
     const int ppp = (hw + parts - 1) / parts;
-    distance_norm_kernel<T><<<grid, DIST_THREADS, 0, st>>>((const T*)act, n_pairs, hw, c, w, ppp, partial);
+    launch_pdl(distance_norm_kernel<T>, dim3(grid), dim3(DIST_THREADS), 0, st, (const T*)act, n_pairs, hw, c, w, ppp, partial);
   } else {
     const int64_t elems = (int64_t)hw * c;
     const int64_t cpp = (elems / 8 + parts - 1) / parts;
     if ((8 * DIST_THREADS) % c == 0)
-      distance_kernel<T, true><<<grid, DIST_THREADS, 0, st>>>((const T*)act, n_pairs, elems, c, w, cpp, partial);
+      launch_pdl(distance_kernel<T, true>, dim3(grid), dim3(DIST_THREADS), 0, st, (const T*)act, n_pairs, elems, c, w, cpp, partial);
     else
-      distance_kernel<T, false><<<grid, DIST_THREADS, 0, st>>>((const T*)act, n_pairs, elems, c, w, cpp, partial);
+      launch_pdl(distance_kernel<T, false>, dim3(grid), dim3(DIST_THREADS), 0, st, (const T*)act, n_pairs, elems, c, w, cpp, partial);
   }
   SEMDIFF_CUDA_OK(cudaGetLastError());
   if (chan_mean != nullptr) {
     dim3 g2((c / 8 + 127) / 128, n_pairs);
-    chan_mean_kernel<T><<<g2, 128, 0, st>>>((const T*)act, n_pairs, hw, c, chan_mean, chan_stride);
+    launch_pdl(chan_mean_kernel<T>, dim3(g2), dim3(128), 0, st, (const T*)act, n_pairs, hw, c, chan_mean, chan_stride);
     SEMDIFF_CUDA_OK(cudaGetLastError());
   }
   return 0;
@@ -224,6 +230,8 @@ struct HeadArgs { int n_parts[MAX_TAPS]; float inv_hw[MAX_TAPS]; };
 __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ partials, int n_taps, int n_pairs,
                                                    HeadArgs args, const float* __restrict__ head_b,
                                                    float* __restrict__ out, float* __restrict__ pre) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
   float total = 0.f;
@@ -243,7 +251,7 @@ int launch_head(const float* partials, int n_taps, int n_pairs, const int* n_par
   if (n_taps < 1 || n_taps > MAX_TAPS || n_pairs <= 0) { set_error("head: n_taps must be in [1,%d]", MAX_TAPS); return SEMDIFF_ERR_ARG; }
   HeadArgs a;
   for (int j = 0; j < n_taps; ++j) { a.n_parts[j] = n_parts[j]; a.inv_hw[j] = 1.f / (float)hw[j]; }
-  head_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(partials, n_taps, n_pairs, a, head_b, out_scores, out_pre_relu);
+  launch_pdl(head_kernel, dim3((n_pairs + 127) / 128), dim3(128), 0, st, partials, n_taps, n_pairs, a, head_b, out_scores, out_pre_relu);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }

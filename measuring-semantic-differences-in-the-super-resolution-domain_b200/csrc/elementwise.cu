@@ -24,6 +24,8 @@ template <typename TIn> __device__ __forceinline__ void load2(const TIn* p, floa
 template <typename T, typename TIn>
 __global__ void __launch_bounds__(256) pack_kernel(const TIn* __restrict__ gt, const TIn* __restrict__ sr,
                                                    int n_pairs, int img0, int n_imgs, int hw, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   const int64_t total = (int64_t)n_imgs * hw;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int img = img0 + (int)(i / hw);
@@ -52,6 +54,8 @@ template <typename T, typename TIn>
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const TIn* __restrict__ gt, const TIn* __restrict__ sr,
                                                        int n_pairs, int img0, int H, int W, T* __restrict__ out,
                                                        int j_real, int off) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   const int H2 = H / 2 + (j_real == 4 ? 3 : 1), W2 = W / 2;
   const int per_img = H2 * W2 * 4;
   const int img = img0 + blockIdx.y;
@@ -97,6 +101,8 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const TIn* __restrict__ g
 template <typename T, typename TIn>
 __global__ void __launch_bounds__(256) pack_s2d16_kernel(const TIn* __restrict__ gt, const TIn* __restrict__ sr, int n_pairs,
                                                          int img0, int H, int W, T* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   const int H2 = H / 2, W2 = W / 2;
   const int per_img = H2 * W2;
   const int img = img0 + blockIdx.y;
@@ -164,6 +170,8 @@ template <typename T> __device__ __forceinline__ uint4 max8(const uint4& a, cons
 template <typename T>
 __global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
                                                       int OH, int OW) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   const int cv = C / 8;
   const int per_img = OH * OW * cv;
   const T* img_in = in + (int64_t)blockIdx.y * H * W * C;
@@ -216,6 +224,8 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const T* __restrict__ in, 
 template <typename T>
 __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int H,
                                                       int W, int C, int win) {
+  pdl_trigger();
+  pdl_wait();  // inputs are the previous kernel's output
   const int cv = C / 8, OH = H / win, OW = W / win;
   const int64_t total = (int64_t)n_img * OH * OW * cv;
   const float inv = 1.f / (float)(win * win);
@@ -253,15 +263,15 @@ static int pack_t(const void* gt_, const void* sr_, int n_pairs, int img0, int n
   if (layout == SEMDIFF_INPUT_S2D16) {
     const int per_img = (H / 2) * (W / 2);
     dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)n_imgs);
-    pack_s2d16_kernel<T, TIn><<<grid, 256, 0, st>>>(gt, sr, n_pairs, img0, H, W, (T*)out);
+    launch_pdl(pack_s2d16_kernel<T, TIn>, dim3(grid), dim3(256), 0, st, gt, sr, n_pairs, img0, H, W, (T*)out);
   } else if (layout == SEMDIFF_INPUT_S2D_ROW4 || layout == SEMDIFF_INPUT_S2D_ROW2) {
     const bool row4 = layout == SEMDIFF_INPUT_S2D_ROW4;
     const int per_img = (H / 2 + (row4 ? 3 : 1)) * (W / 2) * 4;
     dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)n_imgs);
-    pack_s2d_kernel<T, TIn><<<grid, 256, 0, st>>>(gt, sr, n_pairs, img0, H, W, (T*)out, row4 ? 4 : 2, row4 ? 2 : 1);
+    launch_pdl(pack_s2d_kernel<T, TIn>, dim3(grid), dim3(256), 0, st, gt, sr, n_pairs, img0, H, W, (T*)out, row4 ? 4 : 2, row4 ? 2 : 1);
   } else {
     const int64_t total = (int64_t)n_imgs * H * W;
-    pack_kernel<T, TIn><<<grid_for(total, 256), 256, 0, st>>>(gt, sr, n_pairs, img0, n_imgs, H * W, (T*)out);
+    launch_pdl(pack_kernel<T, TIn>, dim3(grid_for(total, 256)), dim3(256), 0, st, gt, sr, n_pairs, img0, n_imgs, H * W, (T*)out);
   }
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
@@ -299,7 +309,7 @@ static int maxpool_t(const void* in, void* out, int n, int H, int W, int C, cuda
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const int per_img = OH * OW * (C / 8);
   dim3 grid((unsigned)std::min((per_img + 255) / 256, 128), (unsigned)n);
-  maxpool_kernel<T><<<grid, 256, 0, st>>>((const T*)in, (T*)out, H, W, C, OH, OW);
+  launch_pdl(maxpool_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)in, (T*)out, H, W, C, OH, OW);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -317,7 +327,7 @@ int launch_maxpool3x3s2(const void* in, void* out, int n, int H, int W, int C, i
 template <typename T>
 static int avgpool_t(const void* in, void* out, int n, int H, int W, int C, int win, cudaStream_t st) {
   const int64_t total = (int64_t)n * (H / win) * (W / win) * (C / 8);
-  avgpool_kernel<T><<<grid_for(total, 256), 256, 0, st>>>((const T*)in, (T*)out, n, H, W, C, win);
+  launch_pdl(avgpool_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T*)in, (T*)out, n, H, W, C, win);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }

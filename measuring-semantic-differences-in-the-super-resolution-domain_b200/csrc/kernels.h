@@ -25,6 +25,19 @@ struct ConvPtrs {
   const void* in; const void* in2; const void* w; const float* bias; const void* res; void* out;
 };
 
+// launch with programmatic stream serialization (see common.cuh pdl_wait / pdl_trigger); only with SEMDIFF_PDL=1 (measured: no gain), else plain launches
+bool pdl_enabled();
+template <typename... P, typename... A>
+inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(args)...);
+}
+
 inline size_t elem_bytes(int precision) { return precision == SEMDIFF_FP32 ? 4 : 2; }
 
 // each returns 0 / negative error code; all asynchronous on `stream`

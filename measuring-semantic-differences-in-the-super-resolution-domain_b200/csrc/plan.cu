@@ -21,6 +21,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// Measured on B200 (profiles/r1_pdl.txt): programmatic dependent launch changes the step time by -1 % (RN50 6.18 -> 6.25 ms,
+// CLIP 8.40 -> 8.53 ms) - the persistent kernels all end within a tile of each other and the plain launch gap is ~1 us -
+// so it is off unless SEMDIFF_PDL=1.
+bool pdl_enabled() {
+  static const bool on = getenv("SEMDIFF_PDL") != nullptr;
+  return on;
+}
+
 struct BufShape { int h = 0, w = 0, c = 0; };
 struct Prepared;
 
