@@ -124,6 +124,14 @@ int semdiff_conv2d(const void* in, const void* weight, const float* bias, const 
                    int32_t stride, int32_t pad, int32_t relu, const void* in2, int32_t H2, int32_t W2, int32_t cin2,
                    int32_t stride2, int32_t pad_hi, int32_t precision, int32_t impl, semdiff_stream_t stream);
 
+/* Stem conv over the SEMDIFF_INPUT_S2D16 layout (cin = 16, cout = 64, stride 1: 4x4 pad 2|1 or 2x2 pad 1|0) with the
+ * following max_pool2d(kernel 3, stride 2, padding 1) computed in the conv epilogue (timm resnet50 conv1+bn1+act1+maxpool):
+ * out = NHWC [n_img, (OH-1)/2+1, (OW-1)/2+1, 64]; the un-pooled conv output is never written.  16-bit precisions, output
+ * width OW <= 128 - (kw - 1).  Same values as semdiff_conv2d followed by semdiff_maxpool3x3s2.  The plan applies this fusion by itself. */
+int semdiff_conv2d_maxpool(const void* in, const void* weight, const float* bias, void* out, int32_t n_img, int32_t H,
+                           int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t pad, int32_t pad_hi,
+                           int32_t relu, int32_t precision, semdiff_stream_t stream);
+
 /* Two chained pointwise convs at a bottleneck boundary, one launch (16-bit precisions only):
  *   out1[m, 256]   = act1(in[m, cin] * w1[:, :cin]^T (+ in2[m, cin2] * w1[:, cin:]^T) + bias1 (+ residual[m, 256]))
  *   out2[m, cout2] = act2(out1 * w2^T + bias2),  cout2 = 64 | 128, cin + cin2 <= 128 (multiples of 64)

@@ -14,6 +14,8 @@
 // 112x112 0.794 -> 0.487 ms against the generic im2col kernel.
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -33,15 +35,23 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
-template <int RG, int ROWB = 128> struct StripCfg {
+// kPool (RG = 4, ROWB = 32 only): the 3x3 stride-2 pad-1 max pool that follows the ResNet stem runs inside the epilogue.
+// The RG * RT conv rows of a tile are staged (16-bit, post-ReLU) in shared memory as before, but instead of being stored
+// they are pooled together with the LAST conv row of the previous tile (kept in a carry buffer): a CTA walks a
+// contiguous range of tiles, top to bottom through each image, so the carry is always the row above - only the first
+// tile of a range that starts inside an image is computed twice (once as a warm-up for its last row).  The
+// 112 x 112 x 64 stem output (822 MB per 256 pairs) never exists in HBM.
+template <int RG, int ROWB = 128, bool kPool = false> struct StripCfg {
   // P = 128 worst case; + slack for the rows that taps shifted in W read beyond the strip (not needed for KW = 1)
   static constexpr int MAX_STRIP = (RG == 1 ? 3 : RG + 3) * 128 * ROWB + ((RG == 1 || ROWB == 32) ? 1024 : 0);
   static constexpr int B_TAP_BYTES = 64 * ROWB;
   static constexpr int B_BYTES = (RG == 1 ? 9 : (ROWB == 32 ? 16 : 4)) * B_TAP_BYTES;
-  static constexpr int C_BUFS = (RG == 1 || ROWB == 32) ? 2 : 1;  // the 64-channel row-window variant has no room for two
+  static constexpr int C_BUFS = kPool ? 1 : ((RG == 1 || ROWB == 32) ? 2 : 1);  // the 64-channel row-window variant has no room for two
   static constexpr int C_BYTES = RG * 128 * 128;
+  static constexpr int POOL_BYTES = RG * 128 * 32;   // (RG * RT / 2) pooled rows of P / 2 pixels: RG * RT * P = RG * 128
+  static constexpr int CARRY_BYTES = 128 * 128;      // one conv row, P <= 128 pixels
   static constexpr int TMEM_COLS = RG * 128;   // 2 stages x RG accumulators x 64 columns
-  static constexpr int SMEM = 2 * MAX_STRIP + B_BYTES + C_BUFS * C_BYTES + 16 * 8 + 16 + 1024;
+  static constexpr int SMEM = 2 * MAX_STRIP + B_BYTES + C_BUFS * C_BYTES + (kPool ? 2 * POOL_BYTES + 2 * CARRY_BYTES : 0) + 16 * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -49,8 +59,10 @@ struct alignas(64) StripParams {
   CUtensorMap tmX;  // input NHWC as (C, W, H, N), box (64, P, RT + 2, 1)
   CUtensorMap tmB;  // weights [64, 576], box (64, 64)
   CUtensorMap tmC;  // output as (64, OW, n_img * OH), box (64, CW, 1): a partial last column block is clipped in OW
+                    // (kPool: the POOLED output as (64, POW, n_img * POH), box (64, POW, 1))
   const float* bias;
   int H, W, OH, OW, P, RT, KH, KW, pad, n_img, tiles_per_img, relu;
+  int POH, POW;     // kPool: pooled output size
   int CW, col_blocks;  // images wider than one strip are cut into column blocks of CW output pixels (then P = 128, RT = 1)
 };
 static_assert(sizeof(StripParams) <= 896, "ConvTcLaunch::params too small");
@@ -74,9 +86,28 @@ template <int ROWB> __device__ __forceinline__ uint64_t strip_desc(uint32_t smem
   return d;
 }
 
-template <typename T, int RG, int ROWB>
+template <typename T> __device__ __forceinline__ uint4 strip_max8(const uint4& a, const uint4& b) {
+  using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
+  uint4 r;
+  const T2* pa = reinterpret_cast<const T2*>(&a);
+  const T2* pb = reinterpret_cast<const T2*>(&b);
+  T2* pr = reinterpret_cast<T2*>(&r);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) pr[k] = __hmax2(pa[k], pb[k]);
+  return r;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& o) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+}
+
+template <typename T, int RG, int ROWB, bool kPool = false>
 __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_constant__ StripParams p) {
-  using Cfg = StripCfg<RG, ROWB>;
+  using Cfg = StripCfg<RG, ROWB, kPool>;
   constexpr int KSTEPS = ROWB / 32;   // K = 16 MMAs per tap
   constexpr int STRIP_MAX_BYTES = Cfg::MAX_STRIP, STRIP_B_BYTES = Cfg::B_BYTES, STRIP_C_BYTES = Cfg::C_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -84,7 +115,9 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
   uint8_t* strip = smem;                                   // [2][STRIP_MAX_BYTES]
   uint8_t* smem_b = smem + 2 * STRIP_MAX_BYTES;            // [taps][64 x 128 B]
   uint8_t* smem_c = smem_b + STRIP_B_BYTES;                // [C_BUFS][RG][128 x 128 B]
-  uint64_t* strip_full = reinterpret_cast<uint64_t*>(smem_c + Cfg::C_BUFS * STRIP_C_BYTES);
+  uint8_t* smem_pool = smem_c + Cfg::C_BUFS * STRIP_C_BYTES;            // kPool: [2][POOL_BYTES] pooled rows, then
+  uint8_t* smem_carry = smem_pool + (kPool ? 2 * Cfg::POOL_BYTES : 0);   //        [2][CARRY_BYTES] last conv row of a tile
+  uint64_t* strip_full = reinterpret_cast<uint64_t*>(smem_carry + (kPool ? 2 * Cfg::CARRY_BYTES : 0));
   uint64_t* strip_empty = strip_full + 2;
   uint64_t* tmem_full = strip_empty + 2;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -96,6 +129,15 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
   const int total_tiles = p.n_img * p.tiles_per_img;
   const int taps = p.KH * p.KW;
   const uint32_t strip_bytes = (uint32_t)(RG * p.RT + p.KH - 1) * p.P * ROWB;
+  // tile schedule: round-robin, or (kPool) a contiguous range per CTA preceded by one warm-up tile when the range
+  // starts below the top of an image
+  int t_first = blockIdx.x, t_begin = blockIdx.x, t_end = total_tiles, t_step = gridDim.x;
+  if (kPool) {
+    t_begin = (int)((int64_t)total_tiles * blockIdx.x / gridDim.x);
+    t_end = (int)((int64_t)total_tiles * (blockIdx.x + 1) / gridDim.x);
+    t_step = 1;
+    t_first = t_begin - ((t_begin < t_end && t_begin % p.tiles_per_img != 0) ? 1 : 0);
+  }
 
   if (warp == 0 && leader) {
     tma_prefetch_desc(&p.tmX); tma_prefetch_desc(&p.tmB); tma_prefetch_desc(&p.tmC);
@@ -119,7 +161,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       for (int t = 0; t < taps; ++t) tma_load_2d(&p.tmB, b_bar, smem_b + t * Cfg::B_TAP_BYTES, t * (ROWB / 2), 0);
       pdl_wait();  // the strips are the previous kernel's output
       int local = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+      for (int tile = t_first; tile < t_end; tile += t_step, ++local) {
         const int b = local & 1, ph = (local >> 1) & 1;
         const int n = tile / p.tiles_per_img, t_in = tile - n * p.tiles_per_img;
         const int rg = t_in / p.col_blocks, cb = t_in - rg * p.col_blocks;
@@ -133,8 +175,8 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
     constexpr uint32_t idesc = umma_idesc_f16(Elem<T>::kUmmaFormat, 128, 64);
     const uint64_t b_desc0 = strip_desc<ROWB>(smem_u32(smem_b));
     int local = 0;
-    if (blockIdx.x < total_tiles) mbar_wait(b_bar, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    if (t_first < t_end) mbar_wait(b_bar, 0);
+    for (int tile = t_first; tile < t_end; tile += t_step, ++local) {
       const int b = local & 1, ph = (local >> 1) & 1;
       mbar_wait(&tmem_empty[b], ph ^ 1);
       mbar_wait(&strip_full[b], ph);
@@ -167,14 +209,16 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
     const int q = warp & 3, v = q * 32 + lane;
     const int set = (warp - 2) >> 2;
     const bool store_thread = (warp == 2 && leader);
+    const int pool_prl0 = kPool ? (int)((threadIdx.x - 64) >> 3) / p.POW : 0;
+    const int pool_pc0 = kPool ? (int)((threadIdx.x - 64) >> 3) - pool_prl0 * p.POW : 0;
     int local = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
+    for (int tile = t_first; tile < t_end; tile += t_step, ++local) {
       const int b = local & 1, ph = (local >> 1) & 1;
       const int n = tile / p.tiles_per_img, t_in = tile - n * p.tiles_per_img;
       const int rg = t_in / p.col_blocks, cb = t_in - rg * p.col_blocks;
       const int oy0 = rg * p.RT * RG, ox0 = cb * p.CW;
       uint8_t* cbuf = smem_c + (Cfg::C_BUFS == 2 ? b : 0) * STRIP_C_BYTES;
-      if (store_thread) bulk_wait_read<Cfg::C_BUFS - 1>();
+      if (store_thread) bulk_wait_read<kPool ? 1 : Cfg::C_BUFS - 1>();   // kPool: the pooled buffer of two tiles ago
       named_bar_sync(1, 256);
       mbar_wait_backoff(&tmem_full[b], ph);
       tcgen05_fence_after();
@@ -212,12 +256,62 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
           }
         }
       }
+      if constexpr (kPool) {
+        // ---- 3x3 / 2 max pool over the staged conv rows (+ the carried row above), torch semantics: padding never wins
+        named_bar_sync(1, 256);   // all conv rows of the tile are staged
+        const int R = RG * p.RT, tid = threadIdx.x - 64;
+        const uint32_t c_addr = smem_u32(cbuf);
+        const uint32_t carry_rd = smem_u32(smem_carry + (local & 1) * Cfg::CARRY_BYTES);
+        const uint32_t carry_wr = smem_u32(smem_carry + ((local + 1) & 1) * Cfg::CARRY_BYTES);
+        const uint32_t pool_addr = smem_u32(smem_pool + (local & 1) * Cfg::POOL_BYTES);
+        const bool warm = tile < t_begin;
+        if (!warm) {
+          // Invalid taps (padding, rows below the image) are replaced by the window centre, which is always valid: max is
+          // idempotent, so the nine loads are unconditional and can all be in flight before the first comparison.
+          const int half_p = p.P >> 1, items = (R >> 1) * p.POW * 8;
+          const uint32_t j = tid & 7;
+          int prl = pool_prl0, pc = pool_pc0;     // pooled row within the tile / pooled column of this thread's item
+          for (int i = tid; i < items; i += 256) {
+            const int r0 = 2 * prl, c0 = 2 * pc;
+            const int rm = oy0 + r0 > 0 ? r0 - 1 : r0, rp = oy0 + r0 + 1 < p.OH ? r0 + 1 : r0;
+            const int cm = c0 > 0 ? c0 - 1 : c0, cp = c0 + 1 < p.OW ? c0 + 1 : c0;
+            const uint32_t row_a[3] = {rm < 0 ? carry_rd : c_addr + (uint32_t)(rm * p.P) * 128, c_addr + (uint32_t)(r0 * p.P) * 128,
+                                       c_addr + (uint32_t)(rp * p.P) * 128};
+            const uint32_t col_o[3] = {(uint32_t)cm * 128 + ((j ^ ((uint32_t)cm & 7)) << 4), (uint32_t)c0 * 128 + ((j ^ ((uint32_t)c0 & 7)) << 4),
+                                       (uint32_t)cp * 128 + ((j ^ ((uint32_t)cp & 7)) << 4)};
+            uint4 v[9];
+#pragma unroll
+            for (int k = 0; k < 9; ++k) v[k] = lds128(row_a[k / 3] + col_o[k % 3]);
+            uint4 m = strip_max8<T>(strip_max8<T>(strip_max8<T>(v[0], v[1]), strip_max8<T>(v[2], v[3])),
+                                    strip_max8<T>(strip_max8<T>(v[4], v[5]), strip_max8<T>(v[6], v[7])));
+            m = strip_max8<T>(m, v[8]);
+            const uint32_t prow = (uint32_t)(prl * half_p + pc);
+            sts128(pool_addr + prow * 128 + ((j ^ (prow & 7)) << 4), m);
+            pc += 32;
+            while (pc >= p.POW) { pc -= p.POW; ++prl; }
+          }
+        }
+        // the tile's last conv row becomes the next tile's row above (other buffer: this tile's pooling may still read its own)
+        for (int i = tid; i < p.P * 8; i += 256) {
+          const uint32_t px = i >> 3, off = ((uint32_t)((i & 7) ^ (px & 7)) << 4);
+          sts128(carry_wr + px * 128 + off, lds128(c_addr + ((uint32_t)(R - 1) * p.P + px) * 128 + off));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 256);
+        if (store_thread && !warm) {
+          const int pr0 = oy0 >> 1;
+          for (int r = 0; r < (R >> 1); ++r)
+            if (pr0 + r < p.POH) tma_store_3d(&p.tmC, smem_pool + (local & 1) * Cfg::POOL_BYTES + r * (p.P >> 1) * 128, 0, 0, n * p.POH + pr0 + r);
+          bulk_commit();
+        }
+      } else {
       fence_proxy_async_smem();
       named_bar_sync(1, 256);
       if (store_thread) {
         for (int oy = 0; oy < RG * p.RT; ++oy)
           if (oy0 + oy < p.OH) tma_store_3d(&p.tmC, cbuf + oy * p.P * 128, 0, ox0, n * p.OH + oy0 + oy);
         bulk_commit();
+      }
       }
     }
     if (store_thread) bulk_wait<0>();
@@ -247,7 +341,20 @@ bool conv_strip_supported(const ConvShape& s, int precision) {
          (int64_t)s.n_img * s.H * s.W < ((int64_t)1 << 31);
 }
 
+static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision, bool pooled);
 int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision) {
+  return strip_prepare(L, q, s, precision, false);
+}
+// stem conv over SEMDIFF_INPUT_S2D16 followed by max_pool2d(3, 2, 1): one strip (no column blocks) per image row
+bool conv_strip_pool_supported(const ConvShape& s, int precision) {
+  return conv_strip_supported(s, precision) && strip_is_s2d16(s) && s.OW() <= 128 - (s.kw - 1);
+}
+int conv_strip_pool_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision) {
+  if (!conv_strip_pool_supported(s, precision)) { set_error("conv_strip_pool: unsupported shape"); return SEMDIFF_ERR_UNSUPPORTED; }
+  return strip_prepare(L, q, s, precision, true);
+}
+
+static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision, bool pooled) {
   if (!conv_strip_supported(s, precision) || q.res != nullptr) { set_error("conv_strip: unsupported shape"); return SEMDIFF_ERR_UNSUPPORTED; }
   static EncodeTiledFn4 enc = nullptr;
   if (enc == nullptr) {
@@ -302,29 +409,32 @@ int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, i
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: weight tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
+  if (pooled && p.col_blocks != 1) { set_error("conv_strip_pool: image wider than one strip"); return SEMDIFF_ERR_UNSUPPORTED; }
+  p.POH = (p.OH - 1) / 2 + 1; p.POW = (p.OW - 1) / 2 + 1;
   {
-    const cuuint64_t dims[3] = {64, (cuuint64_t)p.OW, (cuuint64_t)s.n_img * p.OH};
-    const cuuint64_t strides[2] = {128, (cuuint64_t)p.OW * 128};
-    const cuuint32_t box[3] = {64, (cuuint32_t)p.CW, 1};
+    const int ow = pooled ? p.POW : p.OW, oh = pooled ? p.POH : p.OH;
+    const cuuint64_t dims[3] = {64, (cuuint64_t)ow, (cuuint64_t)s.n_img * oh};
+    const cuuint64_t strides[2] = {128, (cuuint64_t)ow * 128};
+    const cuuint32_t box[3] = {64, (cuuint32_t)(pooled ? p.POW : p.CW), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&p.tmC, dt, 3, q.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: output tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
-  L->block_n = 64; L->a_mode = ROWB == 32 ? 103 : 100 + RG; L->precision = precision;  // 101 / 102: 64-channel strips, RG = 1 / 2; 103: 16-channel
+  L->block_n = 64; L->a_mode = pooled ? 104 : (ROWB == 32 ? 103 : 100 + RG); L->precision = precision;  // 101 / 102: 64-channel strips, RG = 1 / 2; 103: 16-channel; 104: 16-channel + max pool
   return 0;
 }
 
-template <typename T, int RG, int ROWB>
+template <typename T, int RG, int ROWB, bool kPool = false>
 static int strip_launch_t(const StripParams& p, int dev, int sms, cudaStream_t st) {
   static bool configured[64] = {};
-  auto kern = conv3x3_strip_kernel<T, RG, ROWB>;
+  auto kern = conv3x3_strip_kernel<T, RG, ROWB, kPool>;
   if (!configured[dev]) {
-    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StripCfg<RG, ROWB>::SMEM));
+    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StripCfg<RG, ROWB, kPool>::SMEM));
     configured[dev] = true;
   }
   const int tiles = p.n_img * p.tiles_per_img;
-  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(320), StripCfg<RG, ROWB>::SMEM, st, p));
+  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(320), StripCfg<RG, ROWB, kPool>::SMEM, st, p));
   return 0;
 }
 
@@ -336,6 +446,7 @@ int conv_strip_launch(const ConvTcLaunch* L, cudaStream_t st) {
   if (dev < 0 || dev >= 64) dev = 0;
   const bool bf = L->precision == SEMDIFF_BF16;
   switch (L->a_mode) {
+    case 104: return bf ? strip_launch_t<__nv_bfloat16, 4, 32, true>(p, dev, sms, st) : strip_launch_t<__half, 4, 32, true>(p, dev, sms, st);
     case 103: return bf ? strip_launch_t<__nv_bfloat16, 4, 32>(p, dev, sms, st) : strip_launch_t<__half, 4, 32>(p, dev, sms, st);
     case 102: return bf ? strip_launch_t<__nv_bfloat16, 2, 128>(p, dev, sms, st) : strip_launch_t<__half, 2, 128>(p, dev, sms, st);
   }

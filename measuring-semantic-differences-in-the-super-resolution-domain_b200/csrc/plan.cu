@@ -208,6 +208,7 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
   S->fused_away.assign(n_ops, 0);
   // SEMDIFF_NO_CHAIN=1 keeps every conv in its own launch (A/B testing)
   static const bool chain_ok = getenv("SEMDIFF_NO_CHAIN") == nullptr;
+  static const bool pool_ok = getenv("SEMDIFF_NO_POOL_FUSION") == nullptr;
   const int chunk = S->chunk_imgs, tail = chunk > 0 ? (2 * pairs) % chunk : 0;
   for (int i = 0; i < n_ops; ++i) {
     const semdiff_op& op = P->ops[i];
@@ -217,6 +218,26 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
     const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], in_head ? chunk : 2 * pairs);
     const int impl = choose_impl(P, cs);
     S->impl[i] = impl;
+    if (impl == SEMDIFF_CONV_TC_TMA && pool_ok && P->conv_impl == SEMDIFF_CONV_AUTO && chunk == 0 && i + 1 < n_ops &&
+        P->ops[i + 1].kind == SEMDIFF_OP_MAXPOOL3S2 && P->ops[i + 1].src == op.dst && op.res < 0 && op.src2 < 0 &&
+        conv_strip_pool_supported(cs, P->precision)) {
+      // stem conv + max pool in one launch (conv3x3_strip.cu, kPool) - only if nothing else reads the un-pooled stem
+      // output, which is then never written
+      bool dead = true;
+      for (int j = i + 2; j < n_ops && dead; ++j) {
+        const semdiff_op& o = P->ops[j];
+        if (o.src == op.dst || (o.kind == SEMDIFF_OP_CONV && (o.res == op.dst || o.src2 == op.dst))) dead = false;
+        else if (o.kind != SEMDIFF_OP_TAP && o.dst == op.dst) break;   // overwritten before any read
+      }
+      if (dead) {
+        ConvPtrs q = conv_ptrs(op, *S, ws);
+        q.out = ws + S->buf_offset[P->ops[i + 1].dst];
+        int rc = conv_strip_pool_prepare(&S->tc[i], q, cs, P->precision);
+        if (rc != 0) return rc;
+        S->fused_away[i + 1] = 1;
+        continue;
+      }
+    }
     if (impl == SEMDIFF_CONV_TC_TMA && chain_ok && P->conv_impl == SEMDIFF_CONV_AUTO && !in_head) {
       // block boundary in the 256-channel stage: this conv's output tile feeds the next block's first 1x1 conv from
       // shared memory (TAP ops in between only read the output, which is still written in full)
@@ -506,6 +527,19 @@ int semdiff_conv2d(const void* in, const void* weight, const float* bias, const 
   }
   set_error("conv2d: bad impl %d", impl);
   return SEMDIFF_ERR_ARG;
+}
+
+int semdiff_conv2d_maxpool(const void* in, const void* weight, const float* bias, void* out, int32_t n_img, int32_t H,
+                           int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t pad, int32_t pad_hi,
+                           int32_t relu, int32_t precision, semdiff_stream_t st_) {
+  if (in == nullptr || weight == nullptr || bias == nullptr || out == nullptr || n_img <= 0) { set_error("conv2d_maxpool: bad arguments"); return SEMDIFF_ERR_ARG; }
+  ConvShape cs;
+  cs.n_img = n_img; cs.H = H; cs.W = W; cs.cin = cin; cs.cout = cout; cs.kh = kh; cs.kw = kw; cs.stride = 1;
+  cs.pad = pad; cs.relu = relu; cs.pad_hi = pad_hi;
+  ConvTcLaunch L;
+  int rc = conv_strip_pool_prepare(&L, ConvPtrs{in, nullptr, weight, bias, nullptr, out}, cs, precision);
+  if (rc != 0) return rc;
+  return conv_tc_launch(&L, reinterpret_cast<cudaStream_t>(st_));
 }
 
 int semdiff_conv1x1_chain(const void* in, const void* in2, const void* w1, const float* bias1, const void* residual, void* out1,

@@ -123,3 +123,59 @@ def test_conv_tc_many_tiles_persistent():
     case = (4, 28, 28, 128, 128, 3, 1, 1, False)   # K = 1152 -> 18 k-blocks per tile
     out, ref = _conv_case(case, "bf16", _lib.CONV_TC_GATHER, seed=4)
     _check(out, ref, "bf16")
+
+
+POOL_GEOMS = [
+    # n, H, W of the space-to-depth input (= conv output size)
+    (3, 112, 112),   # the 224 x 224 geometry: P = 128, one conv row per row group, 28 tiles per image
+    (300, 16, 24),   # many small images: ranges of contiguous tiles start mid-image on most CTAs (warm-up tiles)
+    (5, 56, 56),     # P = 64: two conv rows per row group
+    (2, 37, 50),     # odd conv height: ragged last tile, pooled row that reaches below the image
+    (2, 9, 125),     # the widest row one strip holds, odd height
+    (1, 4, 8),       # a single tile
+    (150, 112, 8),   # tall, narrow: 28 tiles per image, CTAs change image inside their range
+]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("geom", POOL_GEOMS)
+def test_stem_conv_maxpool_fused(geom, precision):
+    """Stem conv (S2D16 layout) with max_pool2d(3, 2, 1) in the epilogue (csrc/conv3x3_strip.cu, kPool) == the strip conv
+    followed by semdiff_maxpool3x3s2, bit for bit (max of the same 16-bit values), and == torch max_pool2d of it."""
+    import torch
+    from helpers import DT, conv2d, lib, sp
+    n, H, W = geom
+    g = torch.Generator(device="cuda").manual_seed(29 + H + W)
+    dt = DT[precision]
+    x = torch.randn(n, H, W, 16, device="cuda", generator=g).to(dt)
+    w = (torch.randn(64, 4, 4, 16, device="cuda", generator=g) * (2.0 / 256) ** 0.5).to(dt)
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    for relu in (True, False):
+        conv = conv2d(x, w, b, None, 1, 2, relu, precision, _lib.CONV_TC_TMA, pad_hi=1)
+        ph, pw = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        guard = 8192
+        arena = torch.full((n * ph * pw * 64 + 2 * guard,), 123.0, dtype=dt, device="cuda")
+        out = arena[guard:guard + n * ph * pw * 64].view(n, ph, pw, 64)
+        rc = lib().semdiff_conv2d_maxpool(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, H, W, 16, 64, 4, 4, 2, 1,
+                                          int(relu), _lib.PRECISIONS[precision], sp())
+        _lib.check(rc, "semdiff_conv2d_maxpool")
+        torch.cuda.synchronize()
+        assert bool((arena[:guard] == 123.0).all()) and bool((arena[guard + out.numel():] == 123.0).all()), "wrote outside its output"
+        ref = torch.nn.functional.max_pool2d(conv.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1).to(dt)
+        assert torch.equal(out, ref), f"relu={relu}: {(out.float() - ref.float()).abs().max().item()} max abs diff, " \
+                                      f"{int((out != ref).sum())} / {out.numel()} elements"
+        sep = torch.empty_like(ref)
+        _lib.check(lib().semdiff_maxpool3x3s2(conv.data_ptr(), sep.data_ptr(), n, H, W, 64, _lib.PRECISIONS[precision], sp()), "maxpool")
+        torch.cuda.synchronize()
+        assert torch.equal(out, sep)
+
+
+def test_stem_conv_maxpool_unsupported_width():
+    import torch
+    from helpers import lib, sp
+    x = torch.zeros(1, 8, 200, 16, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(64, 4, 4, 16, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(64, device="cuda")
+    out = torch.zeros(1, 4, 100, 64, device="cuda", dtype=torch.bfloat16)
+    rc = lib().semdiff_conv2d_maxpool(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), 1, 8, 200, 16, 64, 4, 4, 2, 1, 1, 0, sp())
+    assert rc == -3 and b"conv_strip_pool" in lib().semdiff_last_error()
