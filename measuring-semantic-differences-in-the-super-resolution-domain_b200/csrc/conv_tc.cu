@@ -13,13 +13,15 @@
 //                 A_IM2COL  kxk / strided convs with Cin % 64 == 0: TMA im2col mode over the NHWC tensor
 //   warp 1      tcgen05.mma issuer (one thread); owns the TMEM allocation (2 accumulator stages)
 //   warps 2-9   epilogue (8 warps = 4 TMEM lane quarters x 2 column halves; 4 warps in the gather variant):
-//               tcgen05.ld -> +bias (+residual) -> ReLU -> 16-bit -> swizzled smem -> TMA store
-//   warp 10     residual loader: TMA-prefetches the residual tile into the smem slot the epilogue will
-//               overwrite in place with the result (ring of slots, freed when the store has read them)
+//               tcgen05.ld -> +bias (+residual) -> ReLU -> 16-bit -> swizzled smem slot; the warps never synchronise
+//               with each other, each publishes its part of the slot on an mbarrier
+//   warp 10     C-ring I/O: TMA store of every staged slot, and as soon as the store has READ the slot, the grant of
+//               the slot to the column group RING ahead - with the TMA prefetch of its residual tile, which the
+//               epilogue then overwrites in place with the result
 //   warps 6-9   (A_GATHER only; the residual loader is then warp 10) software im2col for Cin < 64 (stems): cp.async 16 B chunks into the swizzled
 //               A tile, zero-filling padding / M tail / K tail
 // Pipelines: smem ring full/empty (producers <-> MMA), TMEM full/empty (MMA <-> epilogue),
-//            C ring res_full/c_free (residual loader <-> epilogue/TMA store).
+//            C ring res_full/staged (I/O warp <-> epilogue).
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -99,8 +101,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* res_full_bar = tmem_empty_bar + 2;
-  uint64_t* c_free_bar = res_full_bar + RING;
-  uint64_t* bres_bar = c_free_bar + RING;
+  uint64_t* staged_bar = res_full_bar + RING;
+  uint64_t* bres_bar = staged_bar + RING;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     }
     for (int i = 0; i < RING; ++i) {
       mbar_init(&res_full_bar[i], 1);
-      mbar_init(&c_free_bar[i], 1);
+      mbar_init(&staged_bar[i], EPI_WARPS);
     }
     mbar_init(bres_bar, 1);
     mbar_fence_init();
@@ -222,22 +224,15 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const int q = warp & 3;                              // TMEM lane quarter this warp may touch
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
-    const bool store_thread = (warp == 2 && leader);
-    int local = 0, gc = 0;  // gc: running column-group counter of this CTA (ring position)
+    int local = 0, slot = 0, sphase = 0;  // slot / sphase: position in the C ring
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
       bool tmem_ready = false;
 #pragma unroll 1
-      for (int g = 0; g < Cfg::GROUPS; ++g, ++gc) {
-        const int slot = gc % RING;
+      for (int g = 0; g < Cfg::GROUPS; ++g) {
         uint8_t* cbuf = smem_c + slot * Cfg::GROUP_BYTES;
-        if (p.has_res) {
-          mbar_wait_backoff(&res_full_bar[slot], (gc / RING) & 1);  // residual landed (and the slot is ours)
-        } else {
-          if (store_thread) bulk_wait_read<RING - 1>();      // the store that last used this slot has read it
-          named_bar_sync(1, EPI_WARPS * 32);
-        }
+        mbar_wait_short(&res_full_bar[slot], sphase);  // the slot is ours (and the residual tile, if any, has landed)
         if (!tmem_ready) {
           mbar_wait_backoff(&tmem_full_bar[acc], acc_phase);
           tcgen05_fence_after();
@@ -284,40 +279,55 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
           }
         }
-        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA store (async proxy)
-        named_bar_sync(1, EPI_WARPS * 32);
-        if (store_thread) {
-#pragma unroll
-          for (int b = 0; b < Cfg::BOXES; ++b)
-            tma_store_2d(&p.tmC, cbuf + b * Cfg::BOX_BYTES, n_tile * BLOCK_N + g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
-                         m_tile * BLOCK_M);
-          bulk_commit();
-          if (p.has_res && RING > 1) {
-            bulk_wait_read<1>();  // every store but the one just issued has read its slot
-            if (gc >= 1) mbar_arrive(&c_free_bar[(gc - 1) % RING]);
-          }
-        }
+        // this warp's part of the slot is staged: make it visible to the async proxy (TMA store), then publish
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&staged_bar[slot]);
+        if (++slot == RING) { slot = 0; sphase ^= 1; }
       }
     }
-    if (store_thread) bulk_wait<0>();  // smem must stay valid until the last store has completed
   } else if (warp == (kAMode == A_GATHER ? 10 : 2 + EPI_WARPS)) {
-    // ===================== residual loader =====================
-    if (leader && p.has_res) {
+    // ===================== C-ring I/O: TMA stores of staged slots + slot grants / residual prefetch =====================
+    // One thread owns both directions: a slot is granted to the column group RING ahead as soon as its store has READ
+    // it, and that group's residual tile starts loading at once - RING - 1 groups of HBM latency hidden.
+    if (leader && blockIdx.x < total_tiles) {
       pdl_wait();
-      int gc = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-        for (int g = 0; g < Cfg::GROUPS; ++g, ++gc) {
-          const int slot = gc % RING;
-          mbar_wait(&c_free_bar[slot], ((gc / RING) & 1) ^ 1);
-          mbar_arrive_expect_tx(&res_full_bar[slot], Cfg::GROUP_BYTES);
-          uint8_t* cbuf = smem_c + slot * Cfg::GROUP_BYTES;
+      const int total = Cfg::GROUPS * ((total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
+      int k_load = 0, l_slot = 0, l_g = 0, l_tile = blockIdx.x;
+      int k_store = 0, s_slot = 0, s_phase = 0, s_g = 0, s_tile = blockIdx.x;
+      while (k_store < total) {
+        while (k_load < total && k_load < k_store + RING) {
+          if (p.has_res) {
+            const int m_tile = l_tile / p.n_tiles, n_tile = l_tile - m_tile * p.n_tiles;
+            mbar_arrive_expect_tx(&res_full_bar[l_slot], Cfg::GROUP_BYTES);
+            uint8_t* cbuf = smem_c + l_slot * Cfg::GROUP_BYTES;
+#pragma unroll
+            for (int b = 0; b < Cfg::BOXES; ++b)
+              tma_load_2d(&p.tmR, &res_full_bar[l_slot], cbuf + b * Cfg::BOX_BYTES,
+                          n_tile * BLOCK_N + l_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS, m_tile * BLOCK_M);
+          } else {
+            mbar_arrive(&res_full_bar[l_slot]);
+          }
+          ++k_load;
+          if (++l_slot == RING) l_slot = 0;
+          if (++l_g == Cfg::GROUPS) { l_g = 0; l_tile += gridDim.x; }
+        }
+        mbar_wait(&staged_bar[s_slot], s_phase);
+        {
+          const int m_tile = s_tile / p.n_tiles, n_tile = s_tile - m_tile * p.n_tiles;
+          uint8_t* cbuf = smem_c + s_slot * Cfg::GROUP_BYTES;
 #pragma unroll
           for (int b = 0; b < Cfg::BOXES; ++b)
-            tma_load_2d(&p.tmR, &res_full_bar[slot], cbuf + b * Cfg::BOX_BYTES,
-                        n_tile * BLOCK_N + g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS, m_tile * BLOCK_M);
+            tma_store_2d(&p.tmC, cbuf + b * Cfg::BOX_BYTES, n_tile * BLOCK_N + s_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
+                         m_tile * BLOCK_M);
         }
+        bulk_commit();
+        bulk_wait_read<0>();
+        ++k_store;
+        if (++s_slot == RING) { s_slot = 0; s_phase ^= 1; }
+        if (++s_g == Cfg::GROUPS) { s_g = 0; s_tile += gridDim.x; }
       }
+      bulk_wait<0>();  // smem must stay valid until the last store has completed
     }
   } else {
     // ===================== software im2col gather (128 threads, one A row each) =====================
