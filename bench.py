@@ -306,7 +306,7 @@ def main():
             traffic = json.load(f).get("conv_tc_dram_bytes_per_launch")
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"kernel": "conv_tc_kernel<*> + conv3x3_strip_kernel<*> (tcgen05 implicit GEMM: every conv launch of the trunk)",
+    roofline = {"kernel": "conv_tc_kernel<*> + conv3x3_strip_kernel<*> + conv_chain_kernel<*> (tcgen05 implicit GEMM: every conv launch of the trunk; the stem launch includes the fused max pool)",
                 "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_sustained"], "frac_of_burst_peak": achieved / peaks["bf16_burst"],
                 "traffic": traffic, "peak_source": peaks["source"] + ", sustained bf16 (kernel timed inside a long step)",

@@ -182,19 +182,28 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       mbar_wait(&strip_full[b], ph);
       tcgen05_fence_after();
       if (leader) {
-        const uint32_t sbase = smem_u32(strip + b * STRIP_MAX_BYTES);
+        // The issuing thread's scalar code is on the critical path (one lane, dependent uniform-datapath instructions):
+        // descriptors are built once and advanced by adds - the start-address field (addr >> 4) never carries out of
+        // its 14 bits inside the 227 KB of shared memory.  Before: a division and a full descriptor rebuild per tap and
+        // row group (57 instructions per 4 MMAs in the stem) bounded the kernel.
+        const uint64_t a_base = strip_desc<ROWB>(smem_u32(strip + b * STRIP_MAX_BYTES));
+        const uint32_t s_step = ROWB >> 4, r_step = (uint32_t)(p.P * ROWB) >> 4, g_step = (uint32_t)(p.RT * p.P * ROWB) >> 4;
+        const uint32_t tmem_d0 = tmem_base + b * RG * 64;
+        uint64_t b_desc = b_desc0, a_row = a_base;
+        uint32_t acc_flag = 0;
 #pragma unroll 1
-        for (int tap = 0; tap < taps; ++tap) {
-          const int r = tap / p.KW, s = tap - r * p.KW;
-          const uint64_t b_desc = b_desc0 + (uint64_t)((tap * Cfg::B_TAP_BYTES) >> 4);
+        for (int r = 0; r < p.KH; ++r, a_row += r_step) {
+          uint64_t a_tap = a_row;
+#pragma unroll 1
+          for (int sx = 0; sx < p.KW; ++sx, a_tap += s_step, b_desc += (uint64_t)(Cfg::B_TAP_BYTES >> 4)) {
+            uint64_t a_desc = a_tap;   // view of the strip shifted by (g row groups + r rows, sx pixels)
 #pragma unroll
-          for (int g = 0; g < RG; ++g) {
-            // view of the strip shifted by (g row groups + r rows, s pixels)
-            const uint64_t a_desc = strip_desc<ROWB>(sbase + (uint32_t)((g * p.RT + r) * p.P + s) * ROWB);
-            const uint32_t tmem_d = tmem_base + (b * RG + g) * 64;
+            for (int g = 0; g < RG; ++g, a_desc += g_step) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k)
-              umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (tap | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < KSTEPS; ++k)
+                umma_f16_ss(tmem_d0 + g * 64, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, k == 0 ? acc_flag : 1u);
+            }
+            acc_flag = 1u;
           }
         }
         umma_commit(&strip_empty[b]);

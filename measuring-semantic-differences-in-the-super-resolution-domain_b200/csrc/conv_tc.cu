@@ -12,7 +12,7 @@
 //                 A_TMA     1x1 stride-1 convs: plain 2-D tiled loads of [M, Cin]
 //                 A_IM2COL  kxk / strided convs with Cin % 64 == 0: TMA im2col mode over the NHWC tensor
 //   warp 1      tcgen05.mma issuer (one thread); owns the TMEM allocation (2 accumulator stages)
-//   warps 2-9   epilogue (8 warps = 4 TMEM lane quarters x 2 column halves; 4 warps in the gather variant):
+//   warps 2-9   epilogue (8 warps = 4 TMEM lane quarters x 2 column halves; 4 warps in the gather variant and for 32-wide tiles):
 //               tcgen05.ld -> +bias (+residual) -> ReLU -> 16-bit -> swizzled smem slot; the warps never synchronise
 //               with each other, each publishes its part of the slot on an mbarrier
 //   warp 10     C-ring I/O: TMA store of every staged slot, and as soon as the store has READ the slot, the grant of
@@ -81,7 +81,7 @@ template <int ROW_BYTES> __device__ __forceinline__ uint32_t swz_chunk(uint32_t 
 }
 
 // epilogue warps: 8 (two per TMEM lane quarter, splitting the columns) except where warps 6-9 are the gather producers
-template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int epi_warps() { return (kAMode == A_GATHER || BLOCK_N <= 64) ? 4 : 8; }
+template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int epi_warps() { return (kAMode == A_GATHER || BLOCK_N < 64) ? 4 : 8; }
 template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int cta_threads() {
   return kAMode == A_GATHER ? 352 : (2 + epi_warps<BLOCK_N, kAMode>() + 1) * 32;
 }
