@@ -25,11 +25,11 @@ with open(out_md, "w") as f:
         f.write(f"| {i} | {d['kernel'][:60]} | {int(g(d,'launch__grid_size'))} | {t:.1f} | {100*t/tot:.1f} | "
                 f"{g(d,'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active'):.1f} | {g(d,'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | "
                 f"{g(d,'lts__throughput.avg.pct_of_peak_sustained_elapsed'):.1f} | {(g(d,'dram__bytes_read.sum')+g(d,'dram__bytes_write.sum'))/1e6:.0f} | {int(g(d,'launch__registers_per_thread'))} |\n")
-    conv = [d for d in L if "conv_tc" in d["kernel"] or "conv3x3_strip" in d["kernel"]]
+    conv = [d for d in L if "conv_tc" in d["kernel"] or "conv3x3_strip" in d["kernel"] or "conv_chain" in d["kernel"]]
     ct = sum(g(d, "gpu__time_duration.sum") for d in conv)
     tw = sum(g(d, "gpu__time_duration.sum") * g(d, "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active") for d in conv) / ct
     cb = sum(g(d, "dram__bytes_read.sum") + g(d, "dram__bytes_write.sum") for d in conv)
-    f.write(f"\nTotals: {len(L)} launches, {tot:.0f} us.  conv kernels (conv_tc + conv3x3_strip): {len(conv)} launches, {ct:.0f} us = {100*ct/tot:.1f} % of the step, "
+    f.write(f"\nTotals: {len(L)} launches, {tot:.0f} us.  conv kernels (conv_tc + conv3x3_strip + conv_chain): {len(conv)} launches, {ct:.0f} us = {100*ct/tot:.1f} % of the step, "
             f"time-weighted tensor-pipe utilisation {tw:.1f} %, DRAM traffic {cb/1e9:.2f} GB.\n")
     dist = [d for d in L if "distance" in d["kernel"]]
     f.write(f"distance_kernel: {len(dist)} launches, {sum(g(d,'gpu__time_duration.sum') for d in dist):.0f} us, DRAM "
