@@ -96,6 +96,11 @@ template <typename T> __device__ __forceinline__ uint4 strip_max8(const uint4& a
   for (int k = 0; k < 4; ++k) pr[k] = __hmax2(pa[k], pb[k]);
   return r;
 }
+template <typename T> __device__ __forceinline__ uint32_t strip_max2(uint32_t a, uint32_t b) {
+  using T2 = typename std::conditional<std::is_same<T, __half>::value, __half2, __nv_bfloat162>::type;
+  const T2 r = __hmax2(*reinterpret_cast<const T2*>(&a), *reinterpret_cast<const T2*>(&b));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
@@ -220,6 +225,9 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
     const bool store_thread = (warp == 2 && leader);
     const int pool_prl0 = kPool ? (int)((threadIdx.x - 64) >> 3) / p.POW : 0;
     const int pool_pc0 = kPool ? (int)((threadIdx.x - 64) >> 3) - pool_prl0 * p.POW : 0;
+    uint32_t carry_reg[16];   // kPool, RT == 1: this thread's pixel of the previous tile's last conv row (32 channels, packed)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) carry_reg[k] = 0;
     int local = 0;
     for (int tile = t_first; tile < t_end; tile += t_step, ++local) {
       const int b = local & 1, ph = (local >> 1) & 1;
@@ -231,6 +239,107 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       named_bar_sync(1, 256);
       mbar_wait_backoff(&tmem_full[b], ph);
       tcgen05_fence_after();
+      if constexpr (kPool) {
+        if (p.RT == 1) {
+          // ---- one conv row per row group (P = 128, the 224 x 224 geometry): pool in registers.  A thread owns virtual
+          // pixel v of all four conv rows of the tile (32 channels: `set` picks the half), so the vertical 3-max is a
+          // register max against the row carried from the previous tile, and the horizontal one two warp shuffles (the
+          // left neighbour of lane 0 comes from the previous warp through 128 bytes of shared memory).  Only the pooled
+          // tile is staged: the MMA operand reads keep the shared-memory bandwidth this kernel is bound by.
+          const bool warm = tile < t_begin;
+          uint32_t va[16], vb[16];   // vertical maxima: rows (-1, 0, 1) -> pooled row oy0 / 2, rows (1, 2, 3) -> the next
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (warm && g < 3) continue;   // a warm-up tile only provides the carried row
+            uint32_t acc[32], cur[16];
+            tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + (b * RG + g) * 64 + set * 32, acc);
+            tmem_ld_wait();
+            if (g == 3) {
+              tcgen05_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty[b]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int c0 = set * 32 + j * 8;
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
+              float f[8] = {__uint_as_float(acc[j * 8 + 0]) + b0.x, __uint_as_float(acc[j * 8 + 1]) + b0.y,
+                            __uint_as_float(acc[j * 8 + 2]) + b0.z, __uint_as_float(acc[j * 8 + 3]) + b0.w,
+                            __uint_as_float(acc[j * 8 + 4]) + b1.x, __uint_as_float(acc[j * 8 + 5]) + b1.y,
+                            __uint_as_float(acc[j * 8 + 6]) + b1.z, __uint_as_float(acc[j * 8 + 7]) + b1.w};
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              const uint4 o = pack8<T>(f);
+              cur[j * 4 + 0] = o.x; cur[j * 4 + 1] = o.y; cur[j * 4 + 2] = o.z; cur[j * 4 + 3] = o.w;
+            }
+            const bool valid = oy0 + g < p.OH;   // rows below the image never win (row 0 and, when used, row 2 are valid)
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              if (g == 0) va[k] = oy0 > 0 ? strip_max2<T>(carry_reg[k], cur[k]) : cur[k];
+              if (g == 1) { va[k] = valid ? strip_max2<T>(va[k], cur[k]) : va[k]; vb[k] = cur[k]; }
+              if (g == 2) vb[k] = strip_max2<T>(vb[k], cur[k]);
+              if (g == 3) { vb[k] = valid ? strip_max2<T>(vb[k], cur[k]) : vb[k]; carry_reg[k] = cur[k]; }
+            }
+          }
+          if (!warm) {
+            const uint32_t xch = smem_u32(smem_carry) + (uint32_t)(((local & 1) * 8 + set * 4 + q) * 128);
+            if (lane == 31) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                sts128(xch + k * 16, make_uint4(va[4 * k], va[4 * k + 1], va[4 * k + 2], va[4 * k + 3]));
+                sts128(xch + 64 + k * 16, make_uint4(vb[4 * k], vb[4 * k + 1], vb[4 * k + 2], vb[4 * k + 3]));
+              }
+            }
+            named_bar_sync(2 + set, 128);
+            uint32_t la[16], lb[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              la[k] = __shfl_up_sync(0xffffffffu, va[k], 1);
+              lb[k] = __shfl_up_sync(0xffffffffu, vb[k], 1);
+            }
+            if (lane == 0 && q > 0) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint4 xa = lds128(xch - 128 + k * 16), xb = lds128(xch - 128 + 64 + k * 16);
+                la[4 * k] = xa.x; la[4 * k + 1] = xa.y; la[4 * k + 2] = xa.z; la[4 * k + 3] = xa.w;
+                lb[4 * k] = xb.x; lb[4 * k + 1] = xb.y; lb[4 * k + 2] = xb.z; lb[4 * k + 3] = xb.w;
+              }
+            }
+            const bool lv = v >= 1, rv = v + 1 < p.OW;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const uint32_t ra = __shfl_down_sync(0xffffffffu, va[k], 1), rb = __shfl_down_sync(0xffffffffu, vb[k], 1);
+              uint32_t ma = va[k], mb = vb[k];
+              if (lv) { ma = strip_max2<T>(ma, la[k]); mb = strip_max2<T>(mb, lb[k]); }
+              if (rv) { ma = strip_max2<T>(ma, ra); mb = strip_max2<T>(mb, rb); }
+              va[k] = ma; vb[k] = mb;
+            }
+            if ((v & 1) == 0 && v < p.OW) {   // v is the centre of pooled column v / 2
+              const uint32_t pool_addr = smem_u32(smem_pool + (local & 1) * Cfg::POOL_BYTES);
+              const uint32_t prow_a = (uint32_t)(v >> 1), prow_b = 64u + (uint32_t)(v >> 1);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                sts128(pool_addr + prow_a * 128 + ((uint32_t)((set * 4 + j) ^ (prow_a & 7)) << 4),
+                       make_uint4(va[4 * j], va[4 * j + 1], va[4 * j + 2], va[4 * j + 3]));
+                sts128(pool_addr + prow_b * 128 + ((uint32_t)((set * 4 + j) ^ (prow_b & 7)) << 4),
+                       make_uint4(vb[4 * j], vb[4 * j + 1], vb[4 * j + 2], vb[4 * j + 3]));
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1, 256);
+          if (store_thread && !warm) {
+            const int pr0 = oy0 >> 1;
+            for (int r = 0; r < 2; ++r)
+              if (pr0 + r < p.POH) tma_store_3d(&p.tmC, smem_pool + (local & 1) * Cfg::POOL_BYTES + r * 64 * 128, 0, 0, n * p.POH + pr0 + r);
+            bulk_commit();
+          }
+          continue;
+        }
+      }
       const int g_lo = RG >= 2 ? set * (RG / 2) : 0, g_hi = RG >= 2 ? g_lo + RG / 2 : 1;
       const int u_lo = RG >= 2 ? 0 : set, u_hi = RG >= 2 ? 2 : set + 1;
 #pragma unroll 1
@@ -385,6 +494,7 @@ static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s,
   for (int cand = 128; cand >= 16; cand >>= 1) {
     const int cw_max = cand - (s.kw - 1);
     if (cw_max < 1) continue;
+    if (pooled && cw_max < s.OW()) continue;   // the pooled epilogue needs whole image rows in one strip
     const int rt = 128 / cand;
     const int64_t blocks = (s.OW() + cw_max - 1) / cw_max;
     const int64_t tiles = blocks * ((s.OH() + rt * RG - 1) / (rt * RG));

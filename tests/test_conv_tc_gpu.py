@@ -134,6 +134,9 @@ POOL_GEOMS = [
     (2, 9, 125),     # the widest row one strip holds, odd height
     (1, 4, 8),       # a single tile
     (150, 112, 8),   # tall, narrow: 28 tiles per image, CTAs change image inside their range
+    (40, 30, 100),   # P = 128 (register pooling path): many images, ranges start mid-image, ragged last tile (30 = 7 * 4 + 2)
+    (7, 113, 63),    # P = 128, odd height and odd width: last pooled row / column have two taps
+    (2, 5, 64),      # P = 128 by tie-break, W a power of two
 ]
 
 
