@@ -325,7 +325,7 @@ def main():
             "dtype": args.precision, "data": "synthetic",
             "config": {"workload": f"CLIP-LPIPS regressor, ImageNet RN50 trunk (random init), depth 3, {n} pairs 224x224 per GPU"
                        if args.trunk == "resnet50" else f"CLIP-LPIPS regressor, CLIP-RN50 trunk (random init), depth 3, {n} pairs 224x224 per GPU",
-                       "pairs_per_gpu": n, "microbatch_pairs": model.default_microbatch(H, W), "precision": args.precision,
+                       "pairs_per_gpu": n, "microbatch_pairs": min(model.default_microbatch(H, W), n), "precision": args.precision,
                        "l2": "inputs (2 x %d MB fp32 per step) are larger than the 126 MB L2; no flush needed" % (gt.numel() * 4 >> 20),
                        "collective": "one all_gather_into_tensor of fp32 scores per step" if world > 1 else "none (1 GPU)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,

@@ -475,10 +475,16 @@ static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, con
 static int pick_block_n(int cout, bool has_res, int num_kb, int m_tiles, int sms) {
   if (cout % 128 != 0) return cout % 64 == 0 ? 64 : (cout % 32 == 0 ? 32 : 0);
   if (has_res || cout % 256 != 0) return 128;
-  // 256-wide tiles raise the FLOP per operand byte fetched from L2 (compute-bound convs: K >= 512) but stage their
-  // output through a single smem slot; short-K convs are store-bound and want the 3-slot ring of the 128-wide tile
-  if (num_kb < 8) return 128;
-  return (int64_t)m_tiles * (cout / 256) >= sms ? 256 : 128;
+  // 256-wide tiles raise the FLOP per operand byte fetched from L2 (and halve the activation re-loads of a conv with
+  // several n-tiles) but stage their output through a single smem slot; short-K convs are store-bound and want the
+  // ring of the 128-wide tile.  Measured (profiles/r1_knobs.txt): K = 384 (layer2's conv3 + strided shortcut) 0.217 ->
+  // 0.184 ms with 256-wide tiles.
+  static const int min_kb = getenv("SEMDIFF_N256_MIN_KB") ? atoi(getenv("SEMDIFF_N256_MIN_KB")) : 6;
+  if (num_kb < min_kb) return 128;
+  const int64_t t256 = (int64_t)m_tiles * (cout / 256);
+  if (t256 < sms) return 128;
+  // (falling back to 128-wide tiles when the last wave of 256-wide ones is poorly filled was measured slower: 5.58 -> 5.83 ms)
+  return 256;
 }
 
 static int a_mode_for(const ConvShape& s, int requested) {

@@ -220,12 +220,14 @@ class _B200Scorer(nn.Module):
         return self._plan[stem]
 
     def default_microbatch(self, H: int, W: int) -> int:
-        """Pairs per kernel-program pass.  Measured on B200 (profiles/): per-launch efficiency keeps improving up to
-        ~512 images of 224x224 per launch, which outweighs what L2 residency buys at smaller batches; the count
-        scales inversely with the image area (1024x1024 -> 12 pairs) and bounds the workspace at ~4 GB."""
+        """Pairs per kernel-program pass.  Measured on B200 (profiles/r1_knobs.txt): per-launch efficiency keeps improving
+        with the batch (128 / 256 / 512 pairs per pass: 41.5k / 44.2k / 46.1k pairs/s), which outweighs what L2
+        residency buys at smaller batches; the count scales inversely with the image area (1024x1024 -> 24 pairs) and
+        bounds the workspace at ~8 GB (16-bit modes; the fp32 parity mode keeps 256)."""
         if self.microbatch:
             return int(self.microbatch)
-        return max(1, min(256, (256 * 224 * 224) // max(H * W, 1)))
+        cap = 256 if self.precision == "fp32" else 512
+        return max(1, min(cap, (cap * 224 * 224) // max(H * W, 1)))
 
     def _run(self, a, b, head_w, head_b, want_grad: bool = False):
         n, _, H, W = a.shape

@@ -166,6 +166,21 @@ def test_microbatch_and_batch_position_invariance():
     assert torch.equal(full, ragged) and torch.equal(full, single)
 
 
+def test_default_microbatch_512_pairs_same_scores():
+    """16-bit modes pass up to 512 pairs (1024 images) per kernel-program pass by default: tensors beyond 2^31 bytes,
+    twice the tiles per launch - and a pair's score must not depend on it (one deterministic reduction order per pair)."""
+    oracle, model = oracle_and_module("resnet50", 3, "bf16")
+    assert model.default_microbatch(224, 224) == 512 and model.default_microbatch(1024, 1024) == 24
+    g = torch.Generator(device="cuda").manual_seed(3)
+    gt = torch.randn(520, 3, 224, 224, device="cuda", generator=g)
+    sr = gt + 0.2 * torch.randn(520, 3, 224, 224, device="cuda", generator=g)
+    with torch.no_grad():
+        big = model(gt, sr)               # 512 + 8
+        model.microbatch = 130
+        small = model(gt, sr)
+    assert torch.equal(big, small) and bool(torch.isfinite(big).all()) and float(big.std()) > 0
+
+
 def test_head_gradients():
     oracle, model = oracle_and_module("resnet50", 1, "fp32")
     gt, sr = make_pairs(3, seed=4)
