@@ -35,23 +35,27 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
                : "memory");
 }
 
-// kPool (RG = 4, ROWB = 32 only): the 3x3 stride-2 pad-1 max pool that follows the ResNet stem runs inside the epilogue.
+// kPool = 2 (RG = 1, 64-channel pixels, P = 128): the 2 x 2 average pool that follows the CLIP stem's third conv, in
+// registers: row pairs are consecutive tiles of one CTA (ranges start on even rows), the top row's (a00 + a01) waits in
+// registers for the bottom row, the horizontal neighbour comes by warp shuffle; summation order and the single rounding
+// are those of avgpool_kernel, so the result is bit-identical and the 112 x 112 x 64 conv output is never written.
+// kPool = 1 (RG = 4, ROWB = 32 only): the 3x3 stride-2 pad-1 max pool that follows the ResNet stem runs inside the epilogue.
 // The RG * RT conv rows of a tile are staged (16-bit, post-ReLU) in shared memory as before, but instead of being stored
 // they are pooled together with the LAST conv row of the previous tile (kept in a carry buffer): a CTA walks a
 // contiguous range of tiles, top to bottom through each image, so the carry is always the row above - only the first
 // tile of a range that starts inside an image is computed twice (once as a warm-up for its last row).  The
 // 112 x 112 x 64 stem output (822 MB per 256 pairs) never exists in HBM.
-template <int RG, int ROWB = 128, bool kPool = false> struct StripCfg {
+template <int RG, int ROWB = 128, int kPool = 0> struct StripCfg {
   // P = 128 worst case; + slack for the rows that taps shifted in W read beyond the strip (not needed for KW = 1)
   static constexpr int MAX_STRIP = (RG == 1 ? 3 : RG + 3) * 128 * ROWB + ((RG == 1 || ROWB == 32) ? 1024 : 0);
   static constexpr int B_TAP_BYTES = 64 * ROWB;
   static constexpr int B_BYTES = (RG == 1 ? 9 : (ROWB == 32 ? 16 : 4)) * B_TAP_BYTES;
   static constexpr int C_BUFS = kPool ? 1 : ((RG == 1 || ROWB == 32) ? 2 : 1);  // the 64-channel row-window variant has no room for two
   static constexpr int C_BYTES = RG * 128 * 128;
-  static constexpr int POOL_BYTES = RG * 128 * 32;   // (RG * RT / 2) pooled rows of P / 2 pixels: RG * RT * P = RG * 128
+  static constexpr int POOL_BYTES = kPool == 2 ? 64 * 128 : RG * 128 * 32;   // max: (RG * RT / 2) pooled rows of P / 2 pixels (RG * RT * P = RG * 128); avg: one row of 64
   static constexpr int CARRY_BYTES = 128 * 128;      // one conv row, P <= 128 pixels
   static constexpr int TMEM_COLS = RG * 128;   // 2 stages x RG accumulators x 64 columns
-  static constexpr int SMEM = 2 * MAX_STRIP + B_BYTES + C_BUFS * C_BYTES + (kPool ? 2 * POOL_BYTES + 2 * CARRY_BYTES : 0) + 16 * 8 + 16 + 1024;
+  static constexpr int SMEM = 2 * MAX_STRIP + B_BYTES + C_BUFS * C_BYTES + (kPool ? 2 * POOL_BYTES : 0) + (kPool == 1 ? 2 * CARRY_BYTES : 0) + 16 * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -110,7 +114,7 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& o) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
 }
 
-template <typename T, int RG, int ROWB, bool kPool = false>
+template <typename T, int RG, int ROWB, int kPool = 0>
 __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_constant__ StripParams p) {
   using Cfg = StripCfg<RG, ROWB, kPool>;
   constexpr int KSTEPS = ROWB / 32;   // K = 16 MMAs per tap
@@ -122,7 +126,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
   uint8_t* smem_c = smem_b + STRIP_B_BYTES;                // [C_BUFS][RG][128 x 128 B]
   uint8_t* smem_pool = smem_c + Cfg::C_BUFS * STRIP_C_BYTES;            // kPool: [2][POOL_BYTES] pooled rows, then
   uint8_t* smem_carry = smem_pool + (kPool ? 2 * Cfg::POOL_BYTES : 0);   //        [2][CARRY_BYTES] last conv row of a tile
-  uint64_t* strip_full = reinterpret_cast<uint64_t*>(smem_carry + (kPool ? 2 * Cfg::CARRY_BYTES : 0));
+  uint64_t* strip_full = reinterpret_cast<uint64_t*>(smem_carry + (kPool == 1 ? 2 * Cfg::CARRY_BYTES : 0));
   uint64_t* strip_empty = strip_full + 2;
   uint64_t* tmem_full = strip_empty + 2;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -137,11 +141,16 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
   // tile schedule: round-robin, or (kPool) a contiguous range per CTA preceded by one warm-up tile when the range
   // starts below the top of an image
   int t_first = blockIdx.x, t_begin = blockIdx.x, t_end = total_tiles, t_step = gridDim.x;
-  if (kPool) {
+  if (kPool == 1) {
     t_begin = (int)((int64_t)total_tiles * blockIdx.x / gridDim.x);
     t_end = (int)((int64_t)total_tiles * (blockIdx.x + 1) / gridDim.x);
     t_step = 1;
     t_first = t_begin - ((t_begin < t_end && t_begin % p.tiles_per_img != 0) ? 1 : 0);
+  } else if (kPool == 2) {   // ranges of whole row pairs (one conv row per tile, OH even)
+    t_begin = 2 * (int)((int64_t)(total_tiles / 2) * blockIdx.x / gridDim.x);
+    t_end = 2 * (int)((int64_t)(total_tiles / 2) * (blockIdx.x + 1) / gridDim.x);
+    t_step = 1;
+    t_first = t_begin;
   }
 
   if (warp == 0 && leader) {
@@ -223,9 +232,12 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
     const int q = warp & 3, v = q * 32 + lane;
     const int set = (warp - 2) >> 2;
     const bool store_thread = (warp == 2 && leader);
-    const int pool_prl0 = kPool ? (int)((threadIdx.x - 64) >> 3) / p.POW : 0;
-    const int pool_pc0 = kPool ? (int)((threadIdx.x - 64) >> 3) - pool_prl0 * p.POW : 0;
-    uint32_t carry_reg[16];   // kPool, RT == 1: this thread's pixel of the previous tile's last conv row (32 channels, packed)
+    const int pool_prl0 = kPool == 1 ? (int)((threadIdx.x - 64) >> 3) / p.POW : 0;
+    const int pool_pc0 = kPool == 1 ? (int)((threadIdx.x - 64) >> 3) - pool_prl0 * p.POW : 0;
+    float avg_top[32];        // kPool == 2: (a00 + a01) of the top row of the current 2 x 2 windows
+#pragma unroll
+    for (int k = 0; k < 32; ++k) avg_top[k] = 0.f;
+    uint32_t carry_reg[16];   // kPool == 1, RT == 1: this thread's pixel of the previous tile's last conv row (32 channels, packed)
 #pragma unroll
     for (int k = 0; k < 16; ++k) carry_reg[k] = 0;
     int local = 0;
@@ -239,7 +251,67 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       named_bar_sync(1, 256);
       mbar_wait_backoff(&tmem_full[b], ph);
       tcgen05_fence_after();
-      if constexpr (kPool) {
+      if constexpr (kPool == 2) {
+        // ---- 2 x 2 average pool in registers (one conv row per tile; rows 2k / 2k + 1 are consecutive tiles of this CTA)
+        uint32_t acc[32], cur[16];
+        tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + b * 64 + set * 32, acc);
+        tmem_ld_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[b]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c0 = set * 32 + j * 8;
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c0));
+          const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c0 + 4));
+          float f[8] = {__uint_as_float(acc[j * 8 + 0]) + b0.x, __uint_as_float(acc[j * 8 + 1]) + b0.y,
+                        __uint_as_float(acc[j * 8 + 2]) + b0.z, __uint_as_float(acc[j * 8 + 3]) + b0.w,
+                        __uint_as_float(acc[j * 8 + 4]) + b1.x, __uint_as_float(acc[j * 8 + 5]) + b1.y,
+                        __uint_as_float(acc[j * 8 + 6]) + b1.z, __uint_as_float(acc[j * 8 + 7]) + b1.w};
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          const uint4 o = pack8<T>(f);   // the 16-bit conv output the un-fused pool would read
+          cur[j * 4 + 0] = o.x; cur[j * 4 + 1] = o.y; cur[j * 4 + 2] = o.z; cur[j * 4 + 3] = o.w;
+        }
+        const bool bottom = (oy0 & 1) != 0;
+        uint32_t outp[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const uint32_t nb = __shfl_down_sync(0xffffffffu, cur[k], 1);   // pixel v + 1
+          const T* me = reinterpret_cast<const T*>(&cur[k]);
+          const T* ri = reinterpret_cast<const T*>(&nb);
+          float r2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            // avgpool_kernel's order: ((0 + a00) + a01) + a10) + a11, then * 0.25, one rounding
+            const float t = ((bottom ? avg_top[2 * k + e] : 0.f) + Elem<T>::to_f(me[e])) + Elem<T>::to_f(ri[e]);
+            avg_top[2 * k + e] = t;
+            r2[e] = t * 0.25f;
+          }
+          T* op = reinterpret_cast<T*>(&outp[k]);
+          op[0] = Elem<T>::from_f(r2[0]); op[1] = Elem<T>::from_f(r2[1]);
+        }
+        if (bottom && (v & 1) == 0 && v + 1 < p.OW) {
+          const uint32_t pool_addr = smem_u32(smem_pool + ((local >> 1) & 1) * Cfg::POOL_BYTES);
+          const uint32_t prow = (uint32_t)(v >> 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sts128(pool_addr + prow * 128 + ((uint32_t)((set * 4 + j) ^ (prow & 7)) << 4),
+                   make_uint4(outp[4 * j], outp[4 * j + 1], outp[4 * j + 2], outp[4 * j + 3]));
+        }
+        if (bottom) {
+          fence_proxy_async_smem();
+          named_bar_sync(1, 256);
+          if (store_thread) {
+            tma_store_3d(&p.tmC, smem_pool + ((local >> 1) & 1) * Cfg::POOL_BYTES, 0, 0, n * p.POH + (oy0 >> 1));
+            bulk_commit();
+          }
+        }
+        continue;
+      }
+      if constexpr (kPool == 1) {
         if (p.RT == 1) {
           // ---- one conv row per row group (P = 128, the 224 x 224 geometry): pool in registers.  A thread owns virtual
           // pixel v of all four conv rows of the tile (32 channels: `set` picks the half), so the vertical 3-max is a
@@ -374,7 +446,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
           }
         }
       }
-      if constexpr (kPool) {
+      if constexpr (kPool == 1) {
         // ---- 3x3 / 2 max pool over the staged conv rows (+ the carried row above), torch semantics: padding never wins
         named_bar_sync(1, 256);   // all conv rows of the tile are staged
         const int R = RG * p.RT, tid = threadIdx.x - 64;
@@ -459,9 +531,17 @@ bool conv_strip_supported(const ConvShape& s, int precision) {
          (int64_t)s.n_img * s.H * s.W < ((int64_t)1 << 31);
 }
 
-static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision, bool pooled);
+static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision, int pooled);
 int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision) {
-  return strip_prepare(L, q, s, precision, false);
+  return strip_prepare(L, q, s, precision, 0);
+}
+// 3x3 pad-1 64 -> 64 conv followed by avg_pool2d(2): one conv row per tile (P = 128), row pairs inside one CTA
+bool conv_strip_avgpool_supported(const ConvShape& s, int precision) {
+  return conv_strip_supported(s, precision) && strip_is_3x3(s) && s.OH() % 2 == 0 && s.OW() >= 62 && s.OW() <= 126;
+}
+int conv_strip_avgpool_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision) {
+  if (!conv_strip_avgpool_supported(s, precision)) { set_error("conv_strip_avgpool: unsupported shape"); return SEMDIFF_ERR_UNSUPPORTED; }
+  return strip_prepare(L, q, s, precision, 2);
 }
 // stem conv over SEMDIFF_INPUT_S2D16 followed by max_pool2d(3, 2, 1): one strip (no column blocks) per image row
 bool conv_strip_pool_supported(const ConvShape& s, int precision) {
@@ -469,10 +549,10 @@ bool conv_strip_pool_supported(const ConvShape& s, int precision) {
 }
 int conv_strip_pool_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision) {
   if (!conv_strip_pool_supported(s, precision)) { set_error("conv_strip_pool: unsupported shape"); return SEMDIFF_ERR_UNSUPPORTED; }
-  return strip_prepare(L, q, s, precision, true);
+  return strip_prepare(L, q, s, precision, 1);
 }
 
-static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision, bool pooled) {
+static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision, int pooled) {
   if (!conv_strip_supported(s, precision) || q.res != nullptr) { set_error("conv_strip: unsupported shape"); return SEMDIFF_ERR_UNSUPPORTED; }
   static EncodeTiledFn4 enc = nullptr;
   if (enc == nullptr) {
@@ -495,6 +575,7 @@ static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s,
     const int cw_max = cand - (s.kw - 1);
     if (cw_max < 1) continue;
     if (pooled && cw_max < s.OW()) continue;   // the pooled epilogue needs whole image rows in one strip
+    if (pooled == 2 && cand != 128) continue;  // register avg pool: one conv row per tile
     const int rt = 128 / cand;
     const int64_t blocks = (s.OW() + cw_max - 1) / cw_max;
     const int64_t tiles = blocks * ((s.OH() + rt * RG - 1) / (rt * RG));
@@ -529,7 +610,8 @@ static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s,
     if (r != CUDA_SUCCESS) { set_error("conv_strip: weight tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
   if (pooled && p.col_blocks != 1) { set_error("conv_strip_pool: image wider than one strip"); return SEMDIFF_ERR_UNSUPPORTED; }
-  p.POH = (p.OH - 1) / 2 + 1; p.POW = (p.OW - 1) / 2 + 1;
+  p.POH = pooled == 2 ? p.OH / 2 : (p.OH - 1) / 2 + 1;
+  p.POW = pooled == 2 ? p.OW / 2 : (p.OW - 1) / 2 + 1;
   {
     const int ow = pooled ? p.POW : p.OW, oh = pooled ? p.POH : p.OH;
     const cuuint64_t dims[3] = {64, (cuuint64_t)ow, (cuuint64_t)s.n_img * oh};
@@ -540,11 +622,11 @@ static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: output tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
-  L->block_n = 64; L->a_mode = pooled ? 104 : (ROWB == 32 ? 103 : 100 + RG); L->precision = precision;  // 101 / 102: 64-channel strips, RG = 1 / 2; 103: 16-channel; 104: 16-channel + max pool
+  L->block_n = 64; L->a_mode = pooled == 2 ? 105 : pooled ? 104 : (ROWB == 32 ? 103 : 100 + RG); L->precision = precision;  // 101 / 102: 64-channel strips, RG = 1 / 2; 103: 16-channel; 104: 16-channel + max pool; 105: 3x3 + 2x2 average pool
   return 0;
 }
 
-template <typename T, int RG, int ROWB, bool kPool = false>
+template <typename T, int RG, int ROWB, int kPool = 0>
 static int strip_launch_t(const StripParams& p, int dev, int sms, cudaStream_t st) {
   static bool configured[64] = {};
   auto kern = conv3x3_strip_kernel<T, RG, ROWB, kPool>;
@@ -565,7 +647,8 @@ int conv_strip_launch(const ConvTcLaunch* L, cudaStream_t st) {
   if (dev < 0 || dev >= 64) dev = 0;
   const bool bf = L->precision == SEMDIFF_BF16;
   switch (L->a_mode) {
-    case 104: return bf ? strip_launch_t<__nv_bfloat16, 4, 32, true>(p, dev, sms, st) : strip_launch_t<__half, 4, 32, true>(p, dev, sms, st);
+    case 105: return bf ? strip_launch_t<__nv_bfloat16, 1, 128, 2>(p, dev, sms, st) : strip_launch_t<__half, 1, 128, 2>(p, dev, sms, st);
+    case 104: return bf ? strip_launch_t<__nv_bfloat16, 4, 32, 1>(p, dev, sms, st) : strip_launch_t<__half, 4, 32, 1>(p, dev, sms, st);
     case 103: return bf ? strip_launch_t<__nv_bfloat16, 4, 32>(p, dev, sms, st) : strip_launch_t<__half, 4, 32>(p, dev, sms, st);
     case 102: return bf ? strip_launch_t<__nv_bfloat16, 2, 128>(p, dev, sms, st) : strip_launch_t<__half, 2, 128>(p, dev, sms, st);
   }

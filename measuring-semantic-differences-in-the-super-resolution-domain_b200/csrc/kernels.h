@@ -67,6 +67,9 @@ int conv_strip_launch(const ConvTcLaunch* L, cudaStream_t stream);
 // the space-to-depth stem conv with the following 3x3 stride-2 pad-1 max pool in its epilogue; ptr.out = POOLED output
 bool conv_strip_pool_supported(const ConvShape& s, int precision);
 int conv_strip_pool_prepare(ConvTcLaunch* L, const ConvPtrs& ptr, const ConvShape& s, int precision);
+// a 3x3 pad-1 64 -> 64 conv with the following 2x2 average pool in its epilogue (CLIP stem); ptr.out = POOLED output
+bool conv_strip_avgpool_supported(const ConvShape& s, int precision);
+int conv_strip_avgpool_prepare(ConvTcLaunch* L, const ConvPtrs& ptr, const ConvShape& s, int precision);
 
 // conv1x1 (-> 256 channels, residual or fused shortcut) chained with the next conv1x1 (256 -> 64 | 128): the 256-channel
 // tile is written out AND consumed from shared memory by the second GEMM (conv_chain.cu); conv_tc_launch dispatches to it

@@ -218,11 +218,13 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
     const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], in_head ? chunk : 2 * pairs);
     const int impl = choose_impl(P, cs);
     S->impl[i] = impl;
-    if (impl == SEMDIFF_CONV_TC_TMA && pool_ok && P->conv_impl == SEMDIFF_CONV_AUTO && chunk == 0 && i + 1 < n_ops &&
-        P->ops[i + 1].kind == SEMDIFF_OP_MAXPOOL3S2 && P->ops[i + 1].src == op.dst && op.res < 0 && op.src2 < 0 &&
-        conv_strip_pool_supported(cs, P->precision)) {
-      // stem conv + max pool in one launch (conv3x3_strip.cu, kPool) - only if nothing else reads the un-pooled stem
-      // output, which is then never written
+    const bool next_max = i + 1 < n_ops && P->ops[i + 1].kind == SEMDIFF_OP_MAXPOOL3S2 && conv_strip_pool_supported(cs, P->precision);
+    const bool next_avg = i + 1 < n_ops && P->ops[i + 1].kind == SEMDIFF_OP_AVGPOOL && P->ops[i + 1].stride == 2 &&
+                          conv_strip_avgpool_supported(cs, P->precision);
+    if (impl == SEMDIFF_CONV_TC_TMA && pool_ok && P->conv_impl == SEMDIFF_CONV_AUTO && chunk == 0 && (next_max || next_avg) &&
+        P->ops[i + 1].src == op.dst && op.res < 0 && op.src2 < 0) {
+      // stem conv + max pool (ImageNet trunk) or + 2x2 average pool (CLIP trunk) in one launch (conv3x3_strip.cu, kPool)
+      // - only if nothing else reads the un-pooled conv output, which is then never written
       bool dead = true;
       for (int j = i + 2; j < n_ops && dead; ++j) {
         const semdiff_op& o = P->ops[j];
@@ -232,7 +234,7 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
       if (dead) {
         ConvPtrs q = conv_ptrs(op, *S, ws);
         q.out = ws + S->buf_offset[P->ops[i + 1].dst];
-        int rc = conv_strip_pool_prepare(&S->tc[i], q, cs, P->precision);
+        int rc = next_max ? conv_strip_pool_prepare(&S->tc[i], q, cs, P->precision) : conv_strip_avgpool_prepare(&S->tc[i], q, cs, P->precision);
         if (rc != 0) return rc;
         S->fused_away[i + 1] = 1;
         continue;
@@ -538,6 +540,17 @@ int semdiff_conv2d_maxpool(const void* in, const void* weight, const float* bias
   cs.pad = pad; cs.relu = relu; cs.pad_hi = pad_hi;
   ConvTcLaunch L;
   int rc = conv_strip_pool_prepare(&L, ConvPtrs{in, nullptr, weight, bias, nullptr, out}, cs, precision);
+  if (rc != 0) return rc;
+  return conv_tc_launch(&L, reinterpret_cast<cudaStream_t>(st_));
+}
+
+int semdiff_conv2d_avgpool(const void* in, const void* weight, const float* bias, void* out, int32_t n_img, int32_t H,
+                           int32_t W, int32_t relu, int32_t precision, semdiff_stream_t st_) {
+  if (in == nullptr || weight == nullptr || bias == nullptr || out == nullptr || n_img <= 0) { set_error("conv2d_avgpool: bad arguments"); return SEMDIFF_ERR_ARG; }
+  ConvShape cs;
+  cs.n_img = n_img; cs.H = H; cs.W = W; cs.cin = 64; cs.cout = 64; cs.kh = cs.kw = 3; cs.stride = 1; cs.pad = 1; cs.relu = relu;
+  ConvTcLaunch L;
+  int rc = conv_strip_avgpool_prepare(&L, ConvPtrs{in, nullptr, weight, bias, nullptr, out}, cs, precision);
   if (rc != 0) return rc;
   return conv_tc_launch(&L, reinterpret_cast<cudaStream_t>(st_));
 }

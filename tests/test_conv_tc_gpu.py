@@ -182,3 +182,33 @@ def test_stem_conv_maxpool_unsupported_width():
     out = torch.zeros(1, 4, 100, 64, device="cuda", dtype=torch.bfloat16)
     rc = lib().semdiff_conv2d_maxpool(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), 1, 8, 200, 16, 64, 4, 4, 2, 1, 1, 0, sp())
     assert rc == -3 and b"conv_strip_pool" in lib().semdiff_last_error()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("geom", [(3, 112, 112), (40, 30, 100), (2, 8, 62), (2, 6, 126), (5, 112, 63), (300, 2, 64)])
+def test_conv3x3_avgpool_fused(geom, precision):
+    """3x3 64 -> 64 conv with avg_pool2d(2) in the epilogue (csrc/conv3x3_strip.cu, kPool = 2: CLIP stem.conv3 + stem.pool)
+    == the strip conv followed by semdiff_avgpool, bit for bit (same summation order, one rounding)."""
+    import torch
+    from helpers import DT, conv2d, lib, sp
+    n, H, W = geom
+    g = torch.Generator(device="cuda").manual_seed(31 + H + W)
+    dt = DT[precision]
+    x = torch.randn(n, H, W, 64, device="cuda", generator=g).to(dt)
+    w = (torch.randn(64, 3, 3, 64, device="cuda", generator=g) * (2.0 / 576) ** 0.5).to(dt)
+    b = torch.randn(64, device="cuda", generator=g) * 0.1
+    conv = conv2d(x, w, b, None, 1, 1, True, precision, _lib.CONV_TC_TMA)
+    ph, pw = H // 2, W // 2
+    guard = 8192
+    arena = torch.full((n * ph * pw * 64 + 2 * guard,), 123.0, dtype=dt, device="cuda")
+    out = arena[guard:guard + n * ph * pw * 64].view(n, ph, pw, 64)
+    rc = lib().semdiff_conv2d_avgpool(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, H, W, 1, _lib.PRECISIONS[precision], sp())
+    _lib.check(rc, "semdiff_conv2d_avgpool")
+    torch.cuda.synchronize()
+    assert bool((arena[:guard] == 123.0).all()) and bool((arena[guard + out.numel():] == 123.0).all()), "wrote outside its output"
+    sep = torch.empty_like(out)
+    _lib.check(lib().semdiff_avgpool(conv.data_ptr(), sep.data_ptr(), n, H, W, 64, 2, _lib.PRECISIONS[precision], sp()), "avgpool")
+    torch.cuda.synchronize()
+    assert torch.equal(out, sep), f"{int((out != sep).sum())} / {out.numel()} elements differ, max {(out.float() - sep.float()).abs().max().item()}"
+    ref = torch.nn.functional.avg_pool2d(conv.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
+    assert (out.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()

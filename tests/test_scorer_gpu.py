@@ -108,7 +108,7 @@ def test_chained_block_boundaries_bit_exact(trunk, precision):
         plain = model(gt.cuda(), sr.cuda()).cpu()
         n_plain = model.plan().last_launches()
     print(f"[chain] {trunk} {precision}: {n_plain} -> {n_fused} launches")
-    assert n_plain - n_fused == (4 if trunk == "resnet50" else 3)   # + the stem conv / max pool pair of the ImageNet trunk
+    assert n_plain - n_fused == 4   # three block boundaries + the stem's conv / pool pair (max pool | CLIP: 2x2 average pool)
     assert torch.equal(fused, plain)
 
 
