@@ -132,12 +132,12 @@ int semdiff_conv2d_maxpool(const void* in, const void* weight, const float* bias
                            int32_t W, int32_t cin, int32_t cout, int32_t kh, int32_t kw, int32_t pad, int32_t pad_hi,
                            int32_t relu, int32_t precision, semdiff_stream_t stream);
 
-/* 3x3 stride-1 pad-1 conv, 64 -> 64 channels, with the following avg_pool2d(2) computed in the conv epilogue (timm
+/* 3x3 stride-1 pad-1 conv, cin (32 | 64) -> 64 channels, with the following avg_pool2d(2) computed in the conv epilogue (timm
  * resnet50_clip stem.conv3 + stem.pool): out = NHWC [n_img, H/2, W/2, 64]; the un-pooled conv output is never written.
  * 16-bit precisions, H even, 62 <= W <= 126.  Same values as semdiff_conv2d followed by semdiff_avgpool(window 2).
  * The plan applies this fusion by itself. */
 int semdiff_conv2d_avgpool(const void* in, const void* weight, const float* bias, void* out, int32_t n_img, int32_t H,
-                           int32_t W, int32_t relu, int32_t precision, semdiff_stream_t stream);
+                           int32_t W, int32_t cin, int32_t relu, int32_t precision, semdiff_stream_t stream);
 
 /* Two chained pointwise convs at a bottleneck boundary, one launch (16-bit precisions only):
  *   out1[m, 256]   = act1(in[m, cin] * w1[:, :cin]^T (+ in2[m, cin2] * w1[:, cin:]^T) + bias1 (+ residual[m, 256]))

@@ -45,16 +45,18 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* s
 // contiguous range of tiles, top to bottom through each image, so the carry is always the row above - only the first
 // tile of a range that starts inside an image is computed twice (once as a warm-up for its last row).  The
 // 112 x 112 x 64 stem output (822 MB per 256 pairs) never exists in HBM.
-template <int RG, int ROWB = 128, int kPool = 0> struct StripCfg {
+template <int RG, int ROWB = 128, int kPool = 0, int NC = 64> struct StripCfg {
+  static_assert(NC == 64 || (NC == 32 && kPool == 0), "32 output channels: plain variants only");
   // P = 128 worst case; + slack for the rows that taps shifted in W read beyond the strip (not needed for KW = 1)
   static constexpr int MAX_STRIP = (RG == 1 ? 3 : RG + 3) * 128 * ROWB + ((RG == 1 || ROWB == 32) ? 1024 : 0);
-  static constexpr int B_TAP_BYTES = 64 * ROWB;
+  static constexpr int B_TAP_BYTES = NC * ROWB;
   static constexpr int B_BYTES = (RG == 1 ? 9 : (ROWB == 32 ? 16 : 4)) * B_TAP_BYTES;
   static constexpr int C_BUFS = kPool ? 1 : ((RG == 1 || ROWB == 32) ? 2 : 1);  // the 64-channel row-window variant has no room for two
-  static constexpr int C_BYTES = RG * 128 * 128;
+  static constexpr int C_ROW = NC * 2;               // staged bytes per output pixel
+  static constexpr int C_BYTES = RG * 128 * C_ROW;
   static constexpr int POOL_BYTES = kPool == 2 ? 64 * 128 : RG * 128 * 32;   // max: (RG * RT / 2) pooled rows of P / 2 pixels (RG * RT * P = RG * 128); avg: one row of 64
   static constexpr int CARRY_BYTES = 128 * 128;      // one conv row, P <= 128 pixels
-  static constexpr int TMEM_COLS = RG * 128;   // 2 stages x RG accumulators x 64 columns
+  static constexpr int TMEM_COLS = 2 * RG * NC;   // 2 stages x RG accumulators x NC columns
   static constexpr int SMEM = 2 * MAX_STRIP + B_BYTES + C_BUFS * C_BYTES + (kPool ? 2 * POOL_BYTES : 0) + (kPool == 1 ? 2 * CARRY_BYTES : 0) + 16 * 8 + 16 + 1024;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
@@ -84,9 +86,9 @@ template <int ROWB> __device__ __forceinline__ uint64_t strip_desc(uint32_t smem
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(256 >> 4) << 32;   // SBO: 8 rows x 32 B
+  d |= static_cast<uint64_t>((8 * ROWB) >> 4) << 32;   // SBO: 8 rows x ROWB
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(6) << 61;          // SWIZZLE_32B
+  d |= static_cast<uint64_t>(ROWB == 64 ? 4 : 6) << 61;   // SWIZZLE_64B | SWIZZLE_32B
   return d;
 }
 
@@ -114,9 +116,10 @@ __device__ __forceinline__ void sts128(uint32_t addr, const uint4& o) {
   asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
 }
 
-template <typename T, int RG, int ROWB, int kPool = 0>
+template <typename T, int RG, int ROWB, int kPool = 0, int NC = 64>
 __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_constant__ StripParams p) {
-  using Cfg = StripCfg<RG, ROWB, kPool>;
+  using Cfg = StripCfg<RG, ROWB, kPool, NC>;
+  constexpr int C_ROW = Cfg::C_ROW;
   constexpr int KSTEPS = ROWB / 32;   // K = 16 MMAs per tap
   constexpr int STRIP_MAX_BYTES = Cfg::MAX_STRIP, STRIP_B_BYTES = Cfg::B_BYTES, STRIP_C_BYTES = Cfg::C_BYTES;
   extern __shared__ uint8_t smem_raw[];
@@ -186,7 +189,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc_f16(Elem<T>::kUmmaFormat, 128, 64);
+    constexpr uint32_t idesc = umma_idesc_f16(Elem<T>::kUmmaFormat, 128, NC);
     const uint64_t b_desc0 = strip_desc<ROWB>(smem_u32(smem_b));
     int local = 0;
     if (t_first < t_end) mbar_wait(b_bar, 0);
@@ -202,7 +205,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
         // row group (57 instructions per 4 MMAs in the stem) bounded the kernel.
         const uint64_t a_base = strip_desc<ROWB>(smem_u32(strip + b * STRIP_MAX_BYTES));
         const uint32_t s_step = ROWB >> 4, r_step = (uint32_t)(p.P * ROWB) >> 4, g_step = (uint32_t)(p.RT * p.P * ROWB) >> 4;
-        const uint32_t tmem_d0 = tmem_base + b * RG * 64;
+        const uint32_t tmem_d0 = tmem_base + b * RG * NC;
         uint64_t b_desc = b_desc0, a_row = a_base;
         uint32_t acc_flag = 0;
 #pragma unroll 1
@@ -215,7 +218,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
             for (int g = 0; g < RG; ++g, a_desc += g_step) {
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k)
-                umma_f16_ss(tmem_d0 + g * 64, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, k == 0 ? acc_flag : 1u);
+                umma_f16_ss(tmem_d0 + g * NC, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, k == 0 ? acc_flag : 1u);
             }
             acc_flag = 1u;
           }
@@ -416,17 +419,21 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       const int u_lo = RG >= 2 ? 0 : set, u_hi = RG >= 2 ? 2 : set + 1;
 #pragma unroll 1
       for (int g = g_lo; g < g_hi; ++g) {
-        const uint32_t row_addr = smem_u32(cbuf + g * 128 * 128) + v * 128;
+        const uint32_t row_addr = smem_u32(cbuf + g * 128 * C_ROW) + v * C_ROW;
 #pragma unroll 1
         for (int u = u_lo; u < u_hi; ++u) {
           uint32_t acc[32];
-          tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + (b * RG + g) * 64 + u * 32, acc);
-          tmem_ld_wait();
+          const bool live = u * 32 < NC;   // 32 output channels: the second column unit does not exist
+          if (live) {
+            tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + (b * RG + g) * NC + u * 32, acc);
+            tmem_ld_wait();
+          }
           if (g == g_hi - 1 && u == u_hi - 1) {
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[b]);
           }
+          if (!live) continue;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int c0 = u * 32 + j * 8;
@@ -441,7 +448,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
               for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
             }
             const uint4 o = pack8<T>(f);
-            const uint32_t addr = row_addr + ((uint32_t)((u * 4 + j) ^ (v & 7)) << 4);
+            const uint32_t addr = row_addr + ((uint32_t)((u * 4 + j) ^ (C_ROW == 128 ? (v & 7) : ((v >> 1) & 3))) << 4);
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
           }
         }
@@ -499,7 +506,7 @@ __global__ void __launch_bounds__(320, 1) conv3x3_strip_kernel(const __grid_cons
       named_bar_sync(1, 256);
       if (store_thread) {
         for (int oy = 0; oy < RG * p.RT; ++oy)
-          if (oy0 + oy < p.OH) tma_store_3d(&p.tmC, cbuf + oy * p.P * 128, 0, ox0, n * p.OH + oy0 + oy);
+          if (oy0 + oy < p.OH) tma_store_3d(&p.tmC, cbuf + oy * p.P * C_ROW, 0, ox0, n * p.OH + oy0 + oy);
         bulk_commit();
       }
       }
@@ -519,15 +526,17 @@ typedef CUresult (*EncodeTiledFn4)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static bool strip_is_3x3(const ConvShape& s) { return s.cin == 64 && s.kh == 3 && s.kw == 3 && s.pad == 1 && s.pad_after() == 1; }
+static bool strip_is_3x3(const ConvShape& s) { return (s.cin == 64 || s.cin == 32) && s.kh == 3 && s.kw == 3 && s.pad == 1 && s.pad_after() == 1; }
 static bool strip_is_rowwin(const ConvShape& s) { return s.cin == 64 && s.kw == 1 && s.kh >= 2 && s.kh <= 4 && s.pad == 0 && s.pad_after() == 0; }
 // space-to-depth stems: 7x7/2 pad 3 -> 4x4 (pad 2 | 1), 3x3/2 pad 1 -> 2x2 (pad 1 | 0)
 static bool strip_is_s2d16(const ConvShape& s) {
   return s.cin == 16 && ((s.kh == 4 && s.kw == 4 && s.pad == 2 && s.pad_after() == 1) || (s.kh == 2 && s.kw == 2 && s.pad == 1 && s.pad_after() == 0));
 }
 bool conv_strip_supported(const ConvShape& s, int precision) {
+  // 32 output channels (CLIP stem conv1 / conv2) only where the input rows are narrower than 128 bytes
+  const bool cout_ok = s.cout == 64 || (s.cout == 32 && (s.cin == 32 || s.cin == 16));
   return (precision == SEMDIFF_BF16 || precision == SEMDIFF_FP16) && (strip_is_3x3(s) || strip_is_rowwin(s) || strip_is_s2d16(s)) &&
-         s.stride == 1 && s.cout == 64 && s.cin2 == 0 && s.W >= 6 && s.OH() >= 1 && s.OW() >= 1 &&
+         s.stride == 1 && cout_ok && s.cin2 == 0 && s.W >= 6 && s.OH() >= 1 && s.OW() >= 1 &&
          (int64_t)s.n_img * s.H * s.W < ((int64_t)1 << 31);
 }
 
@@ -537,7 +546,7 @@ int conv_strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, i
 }
 // 3x3 pad-1 64 -> 64 conv followed by avg_pool2d(2): one conv row per tile (P = 128), row pairs inside one CTA
 bool conv_strip_avgpool_supported(const ConvShape& s, int precision) {
-  return conv_strip_supported(s, precision) && strip_is_3x3(s) && s.OH() % 2 == 0 && s.OW() >= 62 && s.OW() <= 126;
+  return conv_strip_supported(s, precision) && strip_is_3x3(s) && s.cout == 64 && s.OH() % 2 == 0 && s.OW() >= 62 && s.OW() <= 126;
 }
 int conv_strip_avgpool_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision) {
   if (!conv_strip_avgpool_supported(s, precision)) { set_error("conv_strip_avgpool: unsupported shape"); return SEMDIFF_ERR_UNSUPPORTED; }
@@ -545,7 +554,7 @@ int conv_strip_avgpool_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvSha
 }
 // stem conv over SEMDIFF_INPUT_S2D16 followed by max_pool2d(3, 2, 1): one strip (no column blocks) per image row
 bool conv_strip_pool_supported(const ConvShape& s, int precision) {
-  return conv_strip_supported(s, precision) && strip_is_s2d16(s) && s.OW() <= 128 - (s.kw - 1);
+  return conv_strip_supported(s, precision) && strip_is_s2d16(s) && s.cout == 64 && s.OW() <= 128 - (s.kw - 1);
 }
 int conv_strip_pool_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int precision) {
   if (!conv_strip_pool_supported(s, precision)) { set_error("conv_strip_pool: unsupported shape"); return SEMDIFF_ERR_UNSUPPORTED; }
@@ -590,7 +599,7 @@ static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s,
   p.tiles_per_img = ((p.OH + p.RT * RG - 1) / (p.RT * RG)) * p.col_blocks;
   const CUtensorMapDataType dt = precision == SEMDIFF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   {
-    const CUtensorMapSwizzle swz = ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B;
+    const CUtensorMapSwizzle swz = ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
     const cuuint64_t dims[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.n_img};
     const cuuint64_t strides[3] = {(cuuint64_t)ROWB, (cuuint64_t)s.W * ROWB, (cuuint64_t)s.H * s.W * ROWB};
     const cuuint32_t box[4] = {(cuuint32_t)s.cin, (cuuint32_t)P, (cuuint32_t)(RG * p.RT + s.kh - 1), 1};
@@ -600,12 +609,12 @@ static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s,
     if (r != CUDA_SUCCESS) { set_error("conv_strip: strip tensor map failed (%d) W=%d H=%d P=%d", (int)r, s.W, s.H, P); return SEMDIFF_ERR_CUDA; }
   }
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)s.K(), 64};
+    const cuuint64_t dims[2] = {(cuuint64_t)s.K(), (cuuint64_t)s.cout};
     const cuuint64_t strides[1] = {(cuuint64_t)s.K() * 2};
-    const cuuint32_t box[2] = {(cuuint32_t)s.cin, 64};
+    const cuuint32_t box[2] = {(cuuint32_t)s.cin, (cuuint32_t)s.cout};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&p.tmB, dt, 2, const_cast<void*>(q.w), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     ROWB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (ROWB == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: weight tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
@@ -614,28 +623,34 @@ static int strip_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s,
   p.POW = pooled == 2 ? p.OW / 2 : (p.OW - 1) / 2 + 1;
   {
     const int ow = pooled ? p.POW : p.OW, oh = pooled ? p.POH : p.OH;
-    const cuuint64_t dims[3] = {64, (cuuint64_t)ow, (cuuint64_t)s.n_img * oh};
-    const cuuint64_t strides[2] = {128, (cuuint64_t)ow * 128};
-    const cuuint32_t box[3] = {64, (cuuint32_t)(pooled ? p.POW : p.CW), 1};
+    const cuuint64_t crow = (cuuint64_t)s.cout * 2;
+    const cuuint64_t dims[3] = {(cuuint64_t)s.cout, (cuuint64_t)ow, (cuuint64_t)s.n_img * oh};
+    const cuuint64_t strides[2] = {crow, (cuuint64_t)ow * crow};
+    const cuuint32_t box[3] = {(cuuint32_t)s.cout, (cuuint32_t)(pooled ? p.POW : p.CW), 1};
     const cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&p.tmC, dt, 3, q.out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     s.cout == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("conv_strip: output tensor map failed (%d)", (int)r); return SEMDIFF_ERR_CUDA; }
   }
-  L->block_n = 64; L->a_mode = pooled == 2 ? 105 : pooled ? 104 : (ROWB == 32 ? 103 : 100 + RG); L->precision = precision;  // 101 / 102: 64-channel strips, RG = 1 / 2; 103: 16-channel; 104: 16-channel + max pool; 105: 3x3 + 2x2 average pool
+  // 101 / 102: 64-channel strips, RG = 1 / 2; 103: 16-channel; 104: 16-channel + max pool; 105: 3x3 + 2x2 average pool;
+  // 106-108: 32-channel input rows (3x3: 32 -> 32, 32 -> 64, 32 -> 64 + average pool); 109: 16-channel, 32 outputs
+  int mode = pooled == 2 ? 105 : pooled ? 104 : (ROWB == 32 ? 103 : 100 + RG);
+  if (ROWB == 64) mode = s.cout == 32 ? 106 : (pooled == 2 ? 108 : 107);
+  if (ROWB == 32 && s.cout == 32) mode = 109;
+  L->block_n = s.cout; L->a_mode = mode; L->precision = precision;
   return 0;
 }
 
-template <typename T, int RG, int ROWB, int kPool = 0>
+template <typename T, int RG, int ROWB, int kPool = 0, int NC = 64>
 static int strip_launch_t(const StripParams& p, int dev, int sms, cudaStream_t st) {
   static bool configured[64] = {};
-  auto kern = conv3x3_strip_kernel<T, RG, ROWB, kPool>;
+  auto kern = conv3x3_strip_kernel<T, RG, ROWB, kPool, NC>;
   if (!configured[dev]) {
-    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StripCfg<RG, ROWB, kPool>::SMEM));
+    SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StripCfg<RG, ROWB, kPool, NC>::SMEM));
     configured[dev] = true;
   }
   const int tiles = p.n_img * p.tiles_per_img;
-  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(320), StripCfg<RG, ROWB, kPool>::SMEM, st, p));
+  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(320), StripCfg<RG, ROWB, kPool, NC>::SMEM, st, p));
   return 0;
 }
 
@@ -647,6 +662,10 @@ int conv_strip_launch(const ConvTcLaunch* L, cudaStream_t st) {
   if (dev < 0 || dev >= 64) dev = 0;
   const bool bf = L->precision == SEMDIFF_BF16;
   switch (L->a_mode) {
+    case 109: return bf ? strip_launch_t<__nv_bfloat16, 4, 32, 0, 32>(p, dev, sms, st) : strip_launch_t<__half, 4, 32, 0, 32>(p, dev, sms, st);
+    case 108: return bf ? strip_launch_t<__nv_bfloat16, 1, 64, 2>(p, dev, sms, st) : strip_launch_t<__half, 1, 64, 2>(p, dev, sms, st);
+    case 107: return bf ? strip_launch_t<__nv_bfloat16, 1, 64>(p, dev, sms, st) : strip_launch_t<__half, 1, 64>(p, dev, sms, st);
+    case 106: return bf ? strip_launch_t<__nv_bfloat16, 1, 64, 0, 32>(p, dev, sms, st) : strip_launch_t<__half, 1, 64, 0, 32>(p, dev, sms, st);
     case 105: return bf ? strip_launch_t<__nv_bfloat16, 1, 128, 2>(p, dev, sms, st) : strip_launch_t<__half, 1, 128, 2>(p, dev, sms, st);
     case 104: return bf ? strip_launch_t<__nv_bfloat16, 4, 32, 1>(p, dev, sms, st) : strip_launch_t<__half, 4, 32, 1>(p, dev, sms, st);
     case 103: return bf ? strip_launch_t<__nv_bfloat16, 4, 32>(p, dev, sms, st) : strip_launch_t<__half, 4, 32>(p, dev, sms, st);

@@ -545,10 +545,10 @@ int semdiff_conv2d_maxpool(const void* in, const void* weight, const float* bias
 }
 
 int semdiff_conv2d_avgpool(const void* in, const void* weight, const float* bias, void* out, int32_t n_img, int32_t H,
-                           int32_t W, int32_t relu, int32_t precision, semdiff_stream_t st_) {
+                           int32_t W, int32_t cin, int32_t relu, int32_t precision, semdiff_stream_t st_) {
   if (in == nullptr || weight == nullptr || bias == nullptr || out == nullptr || n_img <= 0) { set_error("conv2d_avgpool: bad arguments"); return SEMDIFF_ERR_ARG; }
   ConvShape cs;
-  cs.n_img = n_img; cs.H = H; cs.W = W; cs.cin = 64; cs.cout = 64; cs.kh = cs.kw = 3; cs.stride = 1; cs.pad = 1; cs.relu = relu;
+  cs.n_img = n_img; cs.H = H; cs.W = W; cs.cin = cin; cs.cout = 64; cs.kh = cs.kw = 3; cs.stride = 1; cs.pad = 1; cs.relu = relu;
   ConvTcLaunch L;
   int rc = conv_strip_avgpool_prepare(&L, ConvPtrs{in, nullptr, weight, bias, nullptr, out}, cs, precision);
   if (rc != 0) return rc;

@@ -303,14 +303,18 @@ def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True, taps
     st = clip.stem
     c1 = st.conv1.conv
     if s2d_stem and c1.kernel_size == (3, 3) and c1.stride == (2, 2) and c1.padding == (1, 1) and c1.in_channels == 3:
-        # 32-channel stem activations are carried as 64 channels (upper half exactly zero) so that every stem conv
-        # runs on the TMA-im2col tensor-core path (64 channels = one 128-byte swizzle row)
+        # row-window variant: 32-channel stem activations are carried as 64 channels (upper half exactly zero) so that
+        # every stem conv runs on the TMA-im2col tensor-core path (64 channels = one 128-byte swizzle row)
         if s2d_stem == "s2d16":
-            P.stem3_s2d16(c1, st.conv1.bn, IN, T1, cout_pad=64)
+            # strip kernels all the way (csrc/conv3x3_strip.cu): the 32-channel stem activations stay 32 channels wide
+            # (64-byte pixel rows, SWIZZLE_64B) - no zero channels through the tensor pipe or shared memory
+            P.stem3_s2d16(c1, st.conv1.bn, IN, T1, cout_pad=c1.out_channels)
+            P.conv(st.conv2.conv, st.conv2.bn, T1, T2)
+            P.conv(st.conv3.conv, st.conv3.bn, T2, T1)
         else:
             P.stem3_s2d(c1, st.conv1.bn, IN, T1, cout_pad=64)
-        P.conv(st.conv2.conv, st.conv2.bn, T1, T2, cin_pad=64, cout_pad=64)
-        P.conv(st.conv3.conv, st.conv3.bn, T2, T1, cin_pad=64)
+            P.conv(st.conv2.conv, st.conv2.bn, T1, T2, cin_pad=64, cout_pad=64)
+            P.conv(st.conv3.conv, st.conv3.bn, T2, T1, cin_pad=64)
     else:
         P.conv(c1, st.conv1.bn, IN, T1, cin_pad=8)
         P.conv(st.conv2.conv, st.conv2.bn, T1, T2)

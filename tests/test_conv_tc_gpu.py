@@ -185,8 +185,9 @@ def test_stem_conv_maxpool_unsupported_width():
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("cin", [64, 32])
 @pytest.mark.parametrize("geom", [(3, 112, 112), (40, 30, 100), (2, 8, 62), (2, 6, 126), (5, 112, 63), (300, 2, 64)])
-def test_conv3x3_avgpool_fused(geom, precision):
+def test_conv3x3_avgpool_fused(geom, precision, cin):
     """3x3 64 -> 64 conv with avg_pool2d(2) in the epilogue (csrc/conv3x3_strip.cu, kPool = 2: CLIP stem.conv3 + stem.pool)
     == the strip conv followed by semdiff_avgpool, bit for bit (same summation order, one rounding)."""
     import torch
@@ -194,15 +195,15 @@ def test_conv3x3_avgpool_fused(geom, precision):
     n, H, W = geom
     g = torch.Generator(device="cuda").manual_seed(31 + H + W)
     dt = DT[precision]
-    x = torch.randn(n, H, W, 64, device="cuda", generator=g).to(dt)
-    w = (torch.randn(64, 3, 3, 64, device="cuda", generator=g) * (2.0 / 576) ** 0.5).to(dt)
+    x = torch.randn(n, H, W, cin, device="cuda", generator=g).to(dt)
+    w = (torch.randn(64, 3, 3, cin, device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5).to(dt)
     b = torch.randn(64, device="cuda", generator=g) * 0.1
     conv = conv2d(x, w, b, None, 1, 1, True, precision, _lib.CONV_TC_TMA)
     ph, pw = H // 2, W // 2
     guard = 8192
     arena = torch.full((n * ph * pw * 64 + 2 * guard,), 123.0, dtype=dt, device="cuda")
     out = arena[guard:guard + n * ph * pw * 64].view(n, ph, pw, 64)
-    rc = lib().semdiff_conv2d_avgpool(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, H, W, 1, _lib.PRECISIONS[precision], sp())
+    rc = lib().semdiff_conv2d_avgpool(x.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), n, H, W, cin, 1, _lib.PRECISIONS[precision], sp())
     _lib.check(rc, "semdiff_conv2d_avgpool")
     torch.cuda.synchronize()
     assert bool((arena[:guard] == 123.0).all()) and bool((arena[guard + out.numel():] == 123.0).all()), "wrote outside its output"
@@ -212,3 +213,42 @@ def test_conv3x3_avgpool_fused(geom, precision):
     assert torch.equal(out, sep), f"{int((out != sep).sum())} / {out.numel()} elements differ, max {(out.float() - sep.float()).abs().max().item()}"
     ref = torch.nn.functional.avg_pool2d(conv.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1)
     assert (out.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item()
+
+
+STRIP32_CASES = [
+    # n, H, W, cin, cout: 3x3 stride-1 pad-1 over 32-channel pixels (64-byte rows, SWIZZLE_64B): CLIP stem conv2 / conv3
+    (3, 112, 112, 32, 32), (3, 112, 112, 32, 64), (2, 56, 56, 32, 32), (5, 14, 14, 32, 64), (2, 37, 50, 32, 32),
+    (1, 6, 126, 32, 64), (2, 9, 256, 32, 32), (1, 5, 127, 32, 64),
+]
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp16"])
+@pytest.mark.parametrize("case", STRIP32_CASES)
+def test_conv3x3_strip_32_channels(case, precision):
+    import torch
+    from helpers import DT, conv2d, conv_reference
+    n, H, W, cin, cout = case
+    g = torch.Generator(device="cuda").manual_seed(37 + H + W + cout)
+    dt = DT[precision]
+    x = torch.randn(n, H, W, cin, device="cuda", generator=g).to(dt)
+    w = (torch.randn(cout, 3, 3, cin, device="cuda", generator=g) * (2.0 / (9 * cin)) ** 0.5).to(dt)
+    b = torch.randn(cout, device="cuda", generator=g) * 0.1
+    out = conv2d(x, w, b, None, 1, 1, True, precision, _lib.CONV_TC_TMA).double()
+    _check(out, conv_reference(x, w, b, None, 1, 1, True), precision)
+
+
+@pytest.mark.parametrize("geom", [(2, 112, 112), (3, 20, 37), (1, 7, 300)])
+def test_conv_s2d16_clip_stem_strip_32_outputs(geom):
+    """The CLIP 3x3/2 stem conv over SEMDIFF_INPUT_S2D16 with its real 32 output channels (64-byte output rows)."""
+    import torch
+    from helpers import conv2d
+    n, H, W = geom
+    g = torch.Generator(device="cuda").manual_seed(41)
+    x = torch.randn(n, H, W, 16, device="cuda", generator=g).bfloat16()
+    w = (torch.randn(32, 2, 2, 16, device="cuda", generator=g) * (2.0 / 64) ** 0.5).bfloat16()
+    b = torch.randn(32, device="cuda", generator=g) * 0.1
+    out = conv2d(x, w, b, None, 1, 1, True, "bf16", _lib.CONV_TC_TMA, pad_hi=0).double()
+    xp = torch.nn.functional.pad(x.double().permute(0, 3, 1, 2), (1, 0, 1, 0))
+    ref = torch.relu(torch.nn.functional.conv2d(xp, w.double().permute(0, 3, 1, 2), b.double())).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape
+    _check(out, ref, "bf16")
