@@ -649,8 +649,10 @@ static int strip_launch_t(const StripParams& p, int dev, int sms, cudaStream_t s
     SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, StripCfg<RG, ROWB, kPool, NC>::SMEM));
     configured[dev] = true;
   }
-  const int tiles = p.n_img * p.tiles_per_img;
-  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(tiles < sms ? tiles : sms), dim3(320), StripCfg<RG, ROWB, kPool, NC>::SMEM, st, p));
+  // one CTA per SM, never more CTAs than work units (kPool == 2 hands out row PAIRS): a CTA with an empty range would
+  // exit with its resident-weight TMA load still in flight
+  const int units = kPool == 2 ? (p.n_img * p.tiles_per_img) / 2 : p.n_img * p.tiles_per_img;
+  SEMDIFF_CUDA_OK(launch_pdl(kern, dim3(units < sms ? units : sms), dim3(320), StripCfg<RG, ROWB, kPool, NC>::SMEM, st, p));
   return 0;
 }
 
