@@ -140,14 +140,16 @@ int semdiff_conv2d_avgpool(const void* in, const void* weight, const float* bias
                            int32_t W, int32_t cin, int32_t relu, int32_t precision, semdiff_stream_t stream);
 
 /* Two chained pointwise convs at a bottleneck boundary, one launch (16-bit precisions only):
- *   out1[m, 256]   = act1(in[m, cin] * w1[:, :cin]^T (+ in2[m, cin2] * w1[:, cin:]^T) + bias1 (+ residual[m, 256]))
- *   out2[m, cout2] = act2(out1 * w2^T + bias2),  cout2 = 64 | 128, cin + cin2 <= 128 (multiples of 64)
+ *   out1[m, cout1] = act1(in[m, cin] * w1[:, :cin]^T (+ in2[m, cin2] * w1[:, cin:]^T) + bias1 (+ residual[m, cout1]))
+ *   out2[m, cout2] = act2(out1 * w2^T + bias2)
+ * cout1 = 256: cout2 = 64 | 128, cin + cin2 <= 128 (multiples of 64), in2 and residual exclusive (either may be NULL);
+ * cout1 = 512: cin = 128, cout2 = 128, residual required, no in2 (identity blocks of the 512-channel stage).
  * out1 is written in full and consumed by the second conv from shared memory: same values as two semdiff_conv2d
  * calls (timm Bottleneck conv3+bn3+add+act3 followed by the next block's conv1+bn1+act1), one HBM read less.
- * in2 and residual are exclusive and may be NULL (cin2 = 0).  The plan applies this fusion by itself. */
+ * The plan applies this fusion by itself. */
 int semdiff_conv1x1_chain(const void* in, const void* in2, const void* w1, const float* bias1, const void* residual,
                           void* out1, const void* w2, const float* bias2, void* out2, int64_t m, int32_t cin,
-                          int32_t cin2, int32_t cout2, int32_t relu1, int32_t relu2, int32_t precision,
+                          int32_t cin2, int32_t cout1, int32_t cout2, int32_t relu1, int32_t relu2, int32_t precision,
                           semdiff_stream_t stream);
 
 int semdiff_maxpool3x3s2(const void* in, void* out, int32_t n_img, int32_t H, int32_t W, int32_t c,

@@ -40,7 +40,7 @@ SIGNATURES = {
     "semdiff_conv2d": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_conv2d_maxpool": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_conv2d_avgpool": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
-    "semdiff_conv1x1_chain": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _I, _I, _I, _I, _I, _I, _P]),
+    "semdiff_conv1x1_chain": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _I, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_maxpool3x3s2": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "semdiff_avgpool": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_distance_parts": (_I, [_I, _I]),

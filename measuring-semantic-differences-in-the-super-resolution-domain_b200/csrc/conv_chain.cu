@@ -1,7 +1,10 @@
 // Chained pointwise convs of a bottleneck boundary, one kernel, for sm_100a:
 //
-//   y  = relu1( x1 * W1a^T (+ x2 * W1b^T) + b1 (+ res) )        [M, 256]   (conv3 of block i, shortcut fused or residual)
-//   t  = relu2( y * W2^T + b2 )                                  [M, N2]    (conv1 of block i + 1), N2 = 64 | 128
+//   y  = relu1( x1 * W1a^T (+ x2 * W1b^T) + b1 (+ res) )        [M, N1]   (conv3 of block i, shortcut fused or residual)
+//   t  = relu2( y * W2^T + b2 )                                  [M, N2]   (conv1 of block i + 1)
+//   N1 = 256 (G = 2 chunks of 128 columns; W1 and W2 resident in shared memory; N2 = 64 | 128), or
+//   N1 = 512 (G = 4; identity blocks of the 512-channel stage: K1 = 128, N2 = 128; the two 128 KB weight matrices are
+//             streamed per chunk from L2 through one-chunk slots, W2 by its own producer warp)
 //
 // In the 256-channel stage (56 x 56 at 224 x 224 input) both convs are bound by HBM: y is written by the first and read
 // straight back by the second.  Here the 128 x 256 tile of y never leaves the SM between the two: the epilogue of the
@@ -10,7 +13,7 @@
 // consumes exactly the rounded 16-bit values the unfused path would have re-read from HBM.
 // Reference: the timm bottleneck the scorer runs under /root/reference/models/global_eval_models.py:364,371.
 //
-// Roles (352 threads): warp 0 TMA producer (x tiles; W1 / W2 once per CTA, resident), warp 1 tcgen05 issuer
+// Roles (384 threads; warp 11 only loads W2 chunks in the streamed variant): warp 0 TMA producer (x tiles; W1 / W2 once per CTA, resident), warp 1 tcgen05 issuer
 // (GEMM1 per 128-column chunk into 2 TMEM stages, GEMM2 one chunk behind into 2 more), warps 2-9 epilogue
 // (TMEM -> +bias (+residual, in place) -> ReLU -> 16-bit staged tile; no barrier between the warps), warp 10 C-ring I/O
 // (TMA store of each staged slot, residual prefetch into it as soon as the store has read it).  C ring slots cycle
@@ -26,13 +29,13 @@
 namespace semdiff {
 
 namespace chain {
-constexpr int BLOCK_M = 128, N1 = 256, CHUNK = 128, G = N1 / CHUNK;
+constexpr int BLOCK_M = 128, CHUNK = 128;
 constexpr int A_STAGE = BLOCK_M * 64 * 2;       // one 64-channel k-block of a pixel tile
 constexpr int W1_BLOCK = CHUNK * 64 * 2;        // [128 output channels][64 k]
 constexpr int SLOT = BLOCK_M * CHUNK * 2;       // one staged chunk: 2 boxes of [128 px][64 ch]
 constexpr int BOX = BLOCK_M * 64 * 2;
-constexpr int MAX_STAGES = 6, MAX_RING = 4, EPI_WARPS = 8, THREADS = (2 + EPI_WARPS + 1) * 32;
-constexpr int NUM_BARS = 2 * MAX_STAGES + 8 + 4 * MAX_RING + 1;
+constexpr int MAX_STAGES = 6, MAX_RING = 4, EPI_WARPS = 8, THREADS = (2 + EPI_WARPS + 2) * 32;
+constexpr int NUM_BARS = 2 * MAX_STAGES + 8 + 4 * MAX_RING + 1 + 4;
 constexpr int SMEM_LIMIT = 232448;
 }  // namespace chain
 
@@ -40,19 +43,21 @@ struct alignas(64) ChainParams {
   CUtensorMap tmA, tmA2, tmW1, tmW2, tmC, tmR, tmC2;
   const float* bias1;
   const float* bias2;
-  int M, m_tiles, nkb1, nkb_a, has_res, relu1, relu2, stages, ring, smem_bytes, n2;
+  int M, m_tiles, nkb1, nkb_a, has_res, relu1, relu2, stages, ring, smem_bytes, n2, g;
 };
 static_assert(sizeof(ChainParams) <= sizeof(ConvTcLaunch::params), "ConvTcLaunch::params too small");
 
-template <typename T, int N2>
+template <typename T, int N2, int G>
 __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __grid_constant__ ChainParams p) {
   using namespace chain;
+  constexpr int N1 = G * CHUNK;
+  constexpr bool kStream = G > 2;        // weights streamed per chunk instead of resident
   constexpr int W2_BLOCK = N2 * 64 * 2;  // [N2][64 k]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w1 = smem;
-  uint8_t* smem_w2 = smem_w1 + G * p.nkb1 * W1_BLOCK;
-  uint8_t* smem_a = smem_w2 + (N1 / 64) * W2_BLOCK;
+  uint8_t* smem_w2 = smem_w1 + (kStream ? 1 : G) * p.nkb1 * W1_BLOCK;
+  uint8_t* smem_a = smem_w2 + (kStream ? CHUNK / 64 : N1 / 64) * W2_BLOCK;
   uint8_t* smem_c = smem_a + p.stages * A_STAGE;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + p.ring * SLOT);
   uint64_t* empty_bar = full_bar + MAX_STAGES;
@@ -65,7 +70,11 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
   uint64_t* c_ready = c_free + MAX_RING;
   uint64_t* staged = c_ready + MAX_RING;
   uint64_t* w_bar = staged + MAX_RING;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* w1_full = w_bar + 1;   // streamed weights: one chunk slot each, full / empty
+  uint64_t* w1_empty = w1_full + 1;
+  uint64_t* w2_full = w1_empty + 1;
+  uint64_t* w2_empty = w2_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w2_empty + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool leader = elect_one();
@@ -89,6 +98,7 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
       mbar_init(&c_ready[i], EPI_WARPS); mbar_init(&staged[i], EPI_WARPS);
     }
     mbar_init(w_bar, 1);
+    mbar_init(w1_full, 1); mbar_init(w1_empty, 1); mbar_init(w2_full, 1); mbar_init(w2_empty, 1);
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_ptr);
@@ -102,20 +112,37 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (leader) {
-      mbar_arrive_expect_tx(w_bar, G * p.nkb1 * W1_BLOCK + (N1 / 64) * W2_BLOCK);
-      for (int g = 0; g < G; ++g)
-        for (int kb = 0; kb < p.nkb1; ++kb)
-          tma_load_2d(&p.tmW1, w_bar, smem_w1 + (g * p.nkb1 + kb) * W1_BLOCK, kb * 64, g * CHUNK);
-      for (int kb = 0; kb < N1 / 64; ++kb) tma_load_2d(&p.tmW2, w_bar, smem_w2 + kb * W2_BLOCK, kb * 64, 0);
-      pdl_wait();  // x tiles are the previous kernel's output
       int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+      auto load_x = [&](int tile) {   // the x k-blocks of one pixel tile
         for (int kb = 0; kb < p.nkb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], A_STAGE);
           if (kb < p.nkb_a) tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE, kb * 64, tile * BLOCK_M);
           else tma_load_2d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE, (kb - p.nkb_a) * 64, tile * BLOCK_M);
           if (++stage == S) { stage = 0; phase ^= 1; }
+        }
+      };
+      if constexpr (!kStream) {
+        mbar_arrive_expect_tx(w_bar, G * p.nkb1 * W1_BLOCK + (N1 / 64) * W2_BLOCK);
+        for (int g = 0; g < G; ++g)
+          for (int kb = 0; kb < p.nkb1; ++kb)
+            tma_load_2d(&p.tmW1, w_bar, smem_w1 + (g * p.nkb1 + kb) * W1_BLOCK, kb * 64, g * CHUNK);
+        for (int kb = 0; kb < N1 / 64; ++kb) tma_load_2d(&p.tmW2, w_bar, smem_w2 + kb * W2_BLOCK, kb * 64, 0);
+        pdl_wait();  // x tiles are the previous kernel's output
+        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) load_x(tile);
+      } else {
+        // streamed: the W1 chunk of (tile, g) goes into the single slot as soon as GEMM1 of the previous chunk has
+        // retired; the x tile of the NEXT pixel tile is requested right after the first chunk of this one
+        pdl_wait();
+        int n = 0;
+        if (blockIdx.x < p.m_tiles) load_x(blockIdx.x);
+        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
+          for (int g = 0; g < G; ++g, ++n) {
+            mbar_wait(w1_empty, (n & 1) ^ 1);
+            mbar_arrive_expect_tx(w1_full, p.nkb1 * W1_BLOCK);
+            for (int kb = 0; kb < p.nkb1; ++kb) tma_load_2d(&p.tmW1, w1_full, smem_w1 + kb * W1_BLOCK, kb * 64, g * CHUNK);
+            if (g == 0 && tile + (int)gridDim.x < p.m_tiles) load_x(tile + gridDim.x);
+          }
         }
       }
     }
@@ -129,33 +156,37 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
     const uint64_t c_desc0 = umma_smem_desc_sw128(smem_u32(smem_c));
     int stage = 0, phase = 0, slot = 0, c = 0, local = 0;
     uint32_t ready_phase = 0;
-    int prev_slot = -1, prev_g = 0, prev_local = 0;
+    int prev_slot = -1, prev_g = 0, prev_local = 0, c2 = 0;   // c2: GEMM2 chunk counter (streamed W2 slot parity)
     // GEMM2 over one staged chunk of y (runs one chunk behind GEMM1 so that the tensor pipe never waits for the epilogue)
     auto gemm2 = [&](int pslot, int pg, int plocal) {
       const int a2 = plocal & 1;
       if (pg == 0) mbar_wait(&t2_empty[a2], ((plocal >> 1) & 1) ^ 1);
       mbar_wait(&c_ready[pslot], (ready_phase >> pslot) & 1);
       ready_phase ^= 1u << pslot;
+      if (kStream) mbar_wait(w2_full, c2 & 1);
+      ++c2;
       tcgen05_fence_after();
       if (leader) {
         const uint32_t d = tmem_acc2 + a2 * N2;
 #pragma unroll
         for (int j = 0; j < CHUNK / 16; ++j) {
           const uint64_t a_desc = c_desc0 + (uint64_t)((pslot * SLOT + (j >> 2) * BOX) >> 4) + (uint64_t)((j & 3) * 2);
-          const uint64_t b_desc = w2_desc0 + (uint64_t)(((pg * (CHUNK / 64) + (j >> 2)) * W2_BLOCK) >> 4) + (uint64_t)((j & 3) * 2);
+          const uint64_t b_desc = w2_desc0 + (uint64_t)((((kStream ? 0 : pg * (CHUNK / 64)) + (j >> 2)) * W2_BLOCK) >> 4) + (uint64_t)((j & 3) * 2);
           umma_f16_ss(d, a_desc, b_desc, idesc2, (pg | j) != 0 ? 1u : 0u);
         }
         umma_commit(&c_free[pslot]);
+        if (kStream) umma_commit(w2_empty);
         if (pg == G - 1) umma_commit(&t2_full[a2]);
       }
       __syncwarp();
     };
-    if (blockIdx.x < p.m_tiles) mbar_wait(w_bar, 0);
+    if (!kStream && blockIdx.x < p.m_tiles) mbar_wait(w_bar, 0);
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++local) {
       const int stage0 = stage;
       for (int g = 0; g < G; ++g, ++c) {
         const int acc = c & 1;
         mbar_wait(&t1_empty[acc], ((c >> 1) & 1) ^ 1);
+        if (kStream) mbar_wait(w1_full, c & 1);
         tcgen05_fence_after();
         int st = stage0;
         for (int kb = 0; kb < p.nkb1; ++kb) {
@@ -166,12 +197,15 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
           }
           if (leader) {
             const uint64_t a_desc = a_desc0 + (uint64_t)((st * A_STAGE) >> 4);
-            const uint64_t b_desc = w1_desc0 + (uint64_t)(((g * p.nkb1 + kb) * W1_BLOCK) >> 4);
+            const uint64_t b_desc = w1_desc0 + (uint64_t)((((kStream ? 0 : g * p.nkb1) + kb) * W1_BLOCK) >> 4);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_f16_ss(tmem_base + acc * CHUNK, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc1, (kb | k) != 0 ? 1u : 0u);
             if (g == G - 1) umma_commit(&empty_bar[st]);   // both chunks have read this x k-block
-            if (kb == p.nkb1 - 1) umma_commit(&t1_full[acc]);
+            if (kb == p.nkb1 - 1) {
+              umma_commit(&t1_full[acc]);
+              if (kStream) umma_commit(w1_empty);
+            }
           }
           __syncwarp();
           if (++st == S) st = 0;
@@ -226,7 +260,7 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
         if (is_y) mbar_arrive(&c_ready[s]);
       }
     };
-    // phase order per pixel tile i:  y chunk 0 of i,  t of i - 1,  y chunk 1 of i  - GEMM2 of tile i - 1 retires while
+    // phase order per pixel tile i:  y chunk 0 of i,  t of i - 1,  y chunks 1.. of i  - GEMM2 of tile i - 1 retires while
     // chunk 0 of tile i is in the epilogue, so the t phase never waits for the tensor pipe
     auto y_phase = [&](int tile, int g) {
       uint8_t* cbuf = smem_c + slot * SLOT;
@@ -272,11 +306,25 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
       if (++slot == R) { slot = 0; sphase ^= 1; }
     };
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++local) {
-      y_phase(tile, 0);
-      if (local > 0) t_phase(local - 1);
-      y_phase(tile, 1);
+#pragma unroll 1
+      for (int g = 0; g < G; ++g) {
+        y_phase(tile, g);
+        if (g == 0 && local > 0) t_phase(local - 1);
+      }
     }
     if (local > 0) t_phase(local - 1);
+  } else if (warp == 2 + EPI_WARPS + 1) {
+    // ===================== W2 chunk producer (streamed variant only) =====================
+    if (kStream && leader) {
+      int n = 0;
+      for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x)
+        for (int g = 0; g < G; ++g, ++n) {
+          mbar_wait(w2_empty, (n & 1) ^ 1);
+          mbar_arrive_expect_tx(w2_full, (CHUNK / 64) * W2_BLOCK);
+          for (int b = 0; b < CHUNK / 64; ++b)
+            tma_load_2d(&p.tmW2, w2_full, smem_w2 + b * W2_BLOCK, (g * (CHUNK / 64) + b) * 64, 0);
+        }
+    }
   } else {
     // ===================== C-ring I/O: TMA stores of staged slots, then residual prefetch into the freed slot ==========
     // One thread owns both directions, so a slot is handed back as soon as its store has READ it (plus, for y chunks,
@@ -285,15 +333,15 @@ __global__ void __launch_bounds__(chain::THREADS, 1) conv_chain_kernel(const __g
       pdl_wait();
       const int n_local = (p.m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
       const int total = (G + 1) * n_local;
-      // cursor over the phase order: sub 0 = y chunk 0 of tile i, 1 = t of tile i - 1, 2 = y chunk 1 of tile i
+      // cursor over the phase order: sub 0 = y chunk 0 of tile i, 1 = t of tile i - 1, k >= 2 = y chunk k - 1 of tile i
       struct Cursor {
         int i = 0, sub = 0;
         __device__ bool is_y() const { return sub != 1; }
-        __device__ int g() const { return sub >> 1; }
+        __device__ int g() const { return sub == 0 ? 0 : sub - 1; }
         __device__ int local() const { return sub == 1 ? i - 1 : i; }
         __device__ void next(int n) {
           if (sub == 0) sub = i > 0 ? 1 : 2;
-          else if (sub == 1) sub = 2;
+          else if (sub < G) ++sub;
           else { ++i; sub = i < n ? 0 : 1; }
         }
       } ld, stc;
@@ -383,12 +431,17 @@ bool conv_chain_supported(const ConvShape& s1, const ConvShape& s2, bool has_res
   if (precision != SEMDIFF_BF16 && precision != SEMDIFF_FP16) return false;
   const bool pw1 = s1.kh == 1 && s1.kw == 1 && s1.stride == 1 && s1.pad == 0 && s1.pad_after() == 0;
   const bool pw2 = s2.kh == 1 && s2.kw == 1 && s2.stride == 1 && s2.pad == 0 && s2.pad_after() == 0;
-  if (!pw1 || !pw2 || s1.cout != chain::N1 || s2.cin != chain::N1 || s2.cin2 != 0) return false;
-  if (s2.cout != 64 && s2.cout != 128) return false;
-  if (s1.cin % 64 != 0 || s1.cin2 % 64 != 0 || s1.K() > 128) return false;
-  if (s1.cin2 != 0 && (s1.stride2 != 1 || has_res)) return false;
+  if (!pw1 || !pw2 || s2.cin != s1.cout || s2.cin2 != 0) return false;
   if (s1.n_img != s2.n_img || s1.H != s2.H || s1.W != s2.W) return false;
-  return s1.M() > 0 && s1.M() < ((int64_t)1 << 31) - chain::BLOCK_M;
+  if (s1.M() <= 0 || s1.M() >= ((int64_t)1 << 31) - chain::BLOCK_M) return false;
+  if (s1.cout == 256) {   // resident weights
+    if (s2.cout != 64 && s2.cout != 128) return false;
+    if (s1.cin % 64 != 0 || s1.cin2 % 64 != 0 || s1.K() > 128) return false;
+    return s1.cin2 == 0 || (s1.stride2 == 1 && !has_res);
+  }
+  // 512-channel stage, identity blocks: streamed weights (SEMDIFF_NO_CHAIN512=1 keeps these pairs apart)
+  static const bool wide_ok = getenv("SEMDIFF_NO_CHAIN512") == nullptr;
+  return wide_ok && s1.cout == 512 && s2.cout == 128 && s1.cin == 128 && s1.cin2 == 0 && has_res;
 }
 
 int conv_chain_prepare(ConvTcLaunch* L, const ConvPtrs& q1, const ConvShape& s1, const ConvPtrs& q2, const ConvShape& s2,
@@ -400,6 +453,9 @@ int conv_chain_prepare(ConvTcLaunch* L, const ConvPtrs& q1, const ConvShape& s1,
   }
   ChainParams& p = *reinterpret_cast<ChainParams*>(L->params);
   memset(&p, 0, sizeof(p));
+  const int N1 = s1.cout;
+  p.g = N1 / CHUNK;
+  const bool stream = p.g > 2;
   p.M = (int)s1.M();
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.nkb_a = s1.cin / 64;
@@ -408,8 +464,9 @@ int conv_chain_prepare(ConvTcLaunch* L, const ConvPtrs& q1, const ConvShape& s1,
   p.relu1 = s1.relu; p.relu2 = s2.relu;
   p.bias1 = q1.bias; p.bias2 = q2.bias;
   p.n2 = s2.cout;
-  // shared-memory split: resident W1 / W2, then the C ring (residual prefetch depth), the rest to the x ring
-  const int fixed = G * p.nkb1 * W1_BLOCK + (N1 / 64) * p.n2 * 128;
+  // shared-memory split: W1 / W2 (resident, or one chunk slot each when streamed), then the C ring (residual prefetch
+  // depth), the rest to the x ring
+  const int fixed = stream ? p.nkb1 * W1_BLOCK + (CHUNK / 64) * p.n2 * 128 : p.g * p.nkb1 * W1_BLOCK + (N1 / 64) * p.n2 * 128;
   const int avail = SMEM_LIMIT - 1024 - NUM_BARS * 8 - 16 - fixed;
   // measured on B200 (profiles/r1_chain_conv.md): with a residual, 4 slots (3 residual tiles in flight) reach the HBM
   // roofline where 3 lose 13 %; without one the ring only buffers stores
@@ -433,10 +490,10 @@ int conv_chain_prepare(ConvTcLaunch* L, const ConvPtrs& q1, const ConvShape& s1,
   return 0;
 }
 
-template <typename T, int N2>
+template <typename T, int N2, int G>
 static int chain_launch_t(const ChainParams& p, cudaStream_t st) {
   static int configured[64] = {};
-  auto kern = conv_chain_kernel<T, N2>;
+  auto kern = conv_chain_kernel<T, N2, G>;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -452,8 +509,9 @@ static int chain_launch_t(const ChainParams& p, cudaStream_t st) {
 int conv_chain_launch(const ConvTcLaunch* L, cudaStream_t st) {
   const ChainParams& p = *reinterpret_cast<const ChainParams*>(L->params);
   const bool bf = L->precision == SEMDIFF_BF16;
-  if (p.n2 == 64) return bf ? chain_launch_t<__nv_bfloat16, 64>(p, st) : chain_launch_t<__half, 64>(p, st);
-  return bf ? chain_launch_t<__nv_bfloat16, 128>(p, st) : chain_launch_t<__half, 128>(p, st);
+  if (p.g == 4) return bf ? chain_launch_t<__nv_bfloat16, 128, 4>(p, st) : chain_launch_t<__half, 128, 4>(p, st);
+  if (p.n2 == 64) return bf ? chain_launch_t<__nv_bfloat16, 64, 2>(p, st) : chain_launch_t<__half, 64, 2>(p, st);
+  return bf ? chain_launch_t<__nv_bfloat16, 128, 2>(p, st) : chain_launch_t<__half, 128, 2>(p, st);
 }
 
 }  // namespace semdiff

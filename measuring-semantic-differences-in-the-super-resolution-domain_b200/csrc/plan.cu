@@ -556,18 +556,18 @@ int semdiff_conv2d_avgpool(const void* in, const void* weight, const float* bias
 }
 
 int semdiff_conv1x1_chain(const void* in, const void* in2, const void* w1, const float* bias1, const void* residual, void* out1,
-                          const void* w2, const float* bias2, void* out2, int64_t m, int32_t cin, int32_t cin2, int32_t cout2,
-                          int32_t relu1, int32_t relu2, int32_t precision, semdiff_stream_t st_) {
+                          const void* w2, const float* bias2, void* out2, int64_t m, int32_t cin, int32_t cin2, int32_t cout1,
+                          int32_t cout2, int32_t relu1, int32_t relu2, int32_t precision, semdiff_stream_t st_) {
   if (in == nullptr || w1 == nullptr || bias1 == nullptr || out1 == nullptr || w2 == nullptr || bias2 == nullptr || out2 == nullptr ||
       m <= 0 || m >= ((int64_t)1 << 31) || cin <= 0 || cin2 < 0 || (in2 == nullptr) != (cin2 == 0)) {
     set_error("conv1x1_chain: bad arguments");
     return SEMDIFF_ERR_ARG;
   }
   ConvShape s1;  // the pixel dimension is carried as one image of m x 1 pixels
-  s1.n_img = 1; s1.H = (int)m; s1.W = 1; s1.cin = cin; s1.cout = 256; s1.kh = s1.kw = 1; s1.stride = 1; s1.pad = 0; s1.relu = relu1;
+  s1.n_img = 1; s1.H = (int)m; s1.W = 1; s1.cin = cin; s1.cout = cout1; s1.kh = s1.kw = 1; s1.stride = 1; s1.pad = 0; s1.relu = relu1;
   if (in2 != nullptr) { s1.cin2 = cin2; s1.stride2 = 1; s1.H2 = (int)m; s1.W2 = 1; }
   ConvShape s2 = s1;
-  s2.cin = 256; s2.cin2 = 0; s2.cout = cout2; s2.relu = relu2;
+  s2.cin = cout1; s2.cin2 = 0; s2.cout = cout2; s2.relu = relu2;
   ConvTcLaunch L;
   int rc = conv_chain_prepare(&L, ConvPtrs{in, in2, w1, bias1, residual, out1}, s1, ConvPtrs{out1, nullptr, w2, bias2, nullptr, out2}, s2,
                               precision);

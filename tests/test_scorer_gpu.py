@@ -108,7 +108,9 @@ def test_chained_block_boundaries_bit_exact(trunk, precision):
         plain = model(gt.cuda(), sr.cuda()).cpu()
         n_plain = model.plan().last_launches()
     print(f"[chain] {trunk} {precision}: {n_plain} -> {n_fused} launches")
-    assert n_plain - n_fused == 4   # three block boundaries + the stem's conv / pool pair (max pool | CLIP: 2x2 average pool)
+    # 256-channel stage: three block boundaries; 512-channel stage: the two identity-block boundaries; the stem's
+    # conv / pool pair (max pool | CLIP: 2x2 average pool)
+    assert n_plain - n_fused == 6
     assert torch.equal(fused, plain)
 
 
