@@ -82,7 +82,10 @@ typedef struct semdiff_plan semdiff_plan;
 int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision,
                         int32_t input_layout, int32_t head_ops, semdiff_plan** out_plan);
 int semdiff_plan_destroy(semdiff_plan* plan);
-/* Force the conv implementation of every conv op (SEMDIFF_CONV_*; AUTO = best supported). Testing aid. */
+/* Force the conv implementation of every conv op (SEMDIFF_CONV_*; AUTO = best supported). Testing aid.
+ * With AUTO the plan also fuses adjacent ops into single launches where a fused kernel exists (stem conv + pooling
+ * op, conv3 of a bottleneck + conv1 of the next: semdiff_conv2d_maxpool / _avgpool / semdiff_conv1x1_chain below); the
+ * results are bit-identical to one launch per op, which any explicit choice here restores. */
 int semdiff_plan_set_conv_impl(semdiff_plan* plan, int32_t impl);
 
 /* Bytes of device workspace semdiff_score needs for `microbatch_pairs` pairs of HxW images. */
@@ -97,7 +100,7 @@ int64_t semdiff_workspace_bytes(const semdiff_plan* plan, int32_t microbatch_pai
  *   out_pre_relu  device fp32 [n_pairs] or NULL (same value before the final ReLU)
  *   out_chan_mean device fp32 [n_pairs, sum_j C_j] or NULL: per-channel spatial means of (A-B)^2
  *                 (d score / d w_j[c] * n_taps; lets the caller train w_layers, :55-69 of the sweep script)
- * Pairs are processed in micro-batches of `microbatch_pairs` so that activations stay L2-resident. */
+ * Pairs are processed in passes of `microbatch_pairs` pairs (bounds the workspace; a pair's score does not depend on it). */
 int semdiff_score(semdiff_plan* plan, const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H,
                   int32_t W, int32_t microbatch_pairs, const float* head_w, const float* head_b, int32_t normalize,
                   void* workspace, int64_t workspace_bytes, float* out_scores, float* out_pre_relu,
