@@ -183,6 +183,20 @@ def test_default_microbatch_512_pairs_same_scores():
     assert torch.equal(big, small) and bool(torch.isfinite(big).all()) and float(big.std()) > 0
 
 
+def test_forward_is_symmetric_and_zero_on_identical_pairs():
+    """Domain properties of the reference's forward: (a - b)^2 makes it symmetric in its arguments - the
+    callers pass (SR, HQ) - and a pair of identical images scores relu(mean of the biases)."""
+    oracle, model = oracle_and_module("resnet50", 3, "bf16")
+    gt, sr = make_pairs(5, seed=13)
+    gt, sr = gt.cuda(), sr.cuda()
+    with torch.no_grad():
+        ab, ba = model(gt, sr), model(sr, gt)
+        same = model(gt, gt)
+    assert torch.equal(ab, ba)
+    bias = torch.stack([m.bias.detach().reshape(()) for m in model.w_layers]).mean()
+    assert torch.allclose(same, torch.relu(bias).expand(5), rtol=0, atol=1e-7)
+
+
 def test_head_gradients():
     oracle, model = oracle_and_module("resnet50", 1, "fp32")
     gt, sr = make_pairs(3, seed=4)
