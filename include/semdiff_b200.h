@@ -29,8 +29,14 @@ typedef struct CUstream_st* semdiff_stream_t; /* == cudaStream_t */
 
 enum { SEMDIFF_OK = 0, SEMDIFF_ERR_ARG = -1, SEMDIFF_ERR_CUDA = -2, SEMDIFF_ERR_UNSUPPORTED = -3 };
 
-/* storage/compute type of the trunk.  Accumulation is always fp32. */
-enum { SEMDIFF_BF16 = 0, SEMDIFF_FP16 = 1, SEMDIFF_FP32 = 2 };
+/* storage/compute type of the trunk.  Accumulation is always fp32.
+ * The two "x3" types are SPLIT types: every activation and weight is the unevaluated sum hi + lo of two 16-bit numbers
+ * (hi = round(x), lo = round(x - hi): 22 significant bits for fp16, 16 for bf16), and every conv runs as three tensor-core
+ * products per K block, Ah*Wh + Al*Wh + Ah*Wl, into one fp32 accumulator (the Al*Wl term is below fp32 resolution).
+ * Split activations are stored NHWC with 2*C 16-bit channels: for each block of 64 logical channels, 64 hi values then
+ * 64 lo values.  Split conv weights are [Cout][2*K] with the same interleave along K, pre-multiplied by the power of two
+ * semdiff_op.wscale (keeps the lo halves in the normal fp16 range); the epilogue multiplies the accumulator by 1/wscale. */
+enum { SEMDIFF_BF16 = 0, SEMDIFF_FP16 = 1, SEMDIFF_FP32 = 2, SEMDIFF_FP16X3 = 3, SEMDIFF_BF16X3 = 4 };
 
 /* conv implementation selector for semdiff_conv2d (the plan picks AUTO) */
 enum {
@@ -70,8 +76,10 @@ typedef struct semdiff_op {
   int32_t cin2;      /* channels of src2; weight rows are [kh*kw*cin | cin2] */
   int32_t stride2;   /* spatial stride of the fused 1x1 conv over src2 */
   int32_t pad_hi;    /* CONV: padding after the last row/column if it differs from `pad`, else -1 (symmetric) */
-  const void* weight; /* device, [cout][kh][kw][cin] in the plan's precision */
+  const void* weight; /* device, [cout][kh][kw][cin] in the plan's precision (split types: [cout][2*K], see above) */
   const float* bias;  /* device, [cout] fp32 (folded BN shift) */
+  float wscale;       /* split types: the power of two the weights were multiplied by (0 is read as 1) */
+  int32_t reserved;
 } semdiff_op;
 
 typedef struct semdiff_plan semdiff_plan;

@@ -9,8 +9,9 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libsemdiff_b200.so")
 
-BF16, FP16, FP32 = 0, 1, 2
-PRECISIONS = {"bf16": BF16, "fp16": FP16, "fp32": FP32}
+BF16, FP16, FP32, FP16X3, BF16X3 = 0, 1, 2, 3, 4
+PRECISIONS = {"bf16": BF16, "fp16": FP16, "fp32": FP32, "fp16x3": FP16X3, "bf16x3": BF16X3}
+SPLIT = {"fp16x3": "fp16", "bf16x3": "bf16"}   # split precisions -> the 16-bit type of their hi / lo halves
 CONV_AUTO, CONV_SIMT, CONV_TC_GATHER, CONV_TC_TMA = 0, 1, 2, 3
 OP_CONV, OP_MAXPOOL3S2, OP_AVGPOOL, OP_TAP = 0, 1, 2, 3
 MAX_PARTS = 64
@@ -22,7 +23,7 @@ class SemdiffOp(C.Structure):
                 ("cin", C.c_int32), ("cout", C.c_int32), ("kh", C.c_int32), ("kw", C.c_int32),
                 ("stride", C.c_int32), ("pad", C.c_int32), ("relu", C.c_int32), ("tap", C.c_int32),
                 ("src2", C.c_int32), ("cin2", C.c_int32), ("stride2", C.c_int32), ("pad_hi", C.c_int32),
-                ("weight", C.c_void_p), ("bias", C.c_void_p)]
+                ("weight", C.c_void_p), ("bias", C.c_void_p), ("wscale", C.c_float), ("reserved", C.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/semdiff_b200.h declares

@@ -40,7 +40,10 @@ enum { A_TMA = 0, A_GATHER = 1, A_IM2COL = 2 };
 // whose tiles are bound by L2->SM operand traffic, this removes a third of it and doubles the ring depth.
 constexpr int MAX_RES_KB = 9;  // 9 x 64 = 576 = 3x3x64
 
-template <int BLOCK_N, bool kBRes = false> struct TcCfg {
+// kSplit: split precisions (hi + lo pairs of 16-bit numbers, include/semdiff_b200.h).  Every original K block is three
+// ring fills, (A hi, W hi), (A lo, W hi), (A hi, W lo), into the same accumulator; the output tile is written as 64-column
+// groups of two boxes, [64 hi | 64 lo] = 128 consecutive 16-bit columns of the [M, 2 Cout] output.
+template <int BLOCK_N, bool kBRes = false, bool kSplit = false> struct TcCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + (kBRes ? 0 : B_STAGE_BYTES);
   static constexpr int STAGES = kBRes ? 6 : (BLOCK_N >= 128 ? 4 : 6);
@@ -49,12 +52,13 @@ template <int BLOCK_N, bool kBRes = false> struct TcCfg {
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   // epilogue staging: the tile is written out in column groups, each group = BOXES TMA boxes of BOX_COLS columns
   static constexpr int BOX_COLS = BLOCK_N < 64 ? BLOCK_N : 64;
-  static constexpr int GROUP_COLS = BLOCK_N < 128 ? BLOCK_N : 128;
+  static constexpr int GROUP_COLS = kSplit ? 64 : (BLOCK_N < 128 ? BLOCK_N : 128);   // accumulator columns per group
   static constexpr int GROUPS = BLOCK_N / GROUP_COLS;
-  static constexpr int BOXES = GROUP_COLS / BOX_COLS;   // per group
+  static constexpr int BOXES = kSplit ? 2 : GROUP_COLS / BOX_COLS;   // per group
+  static_assert(!kSplit || (BLOCK_N >= 64 && !kBRes), "split tiles: 64-column hi / lo boxes, ring-fed weights");
   static constexpr int BOX_BYTES = BLOCK_M * BOX_COLS * 2;
   static constexpr int GROUP_BYTES = BOXES * BOX_BYTES;
-  static constexpr int RING = BLOCK_N == 256 ? 1 : 3;   // BLOCK_N == 256 never carries a residual
+  static constexpr int RING = BLOCK_N == 256 ? 1 : (kSplit && BLOCK_N == 64 ? 2 : 3);   // non-split BLOCK_N == 256 never carries a residual
   static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RING + 1;
   static constexpr int SMEM_BYTES = STAGES * A_STAGE_BYTES + B_REGION_BYTES + RING * GROUP_BYTES + NUM_BARS * 8 + 16 + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
@@ -71,6 +75,9 @@ struct alignas(64) ConvTcParams {
   int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, relu, has_res;
   int M, num_kb, m_tiles, n_tiles, cpt, taps;
   int num_kb1, a2_im2col, stride2;  // k-blocks [num_kb1, num_kb) come from the second source
+  // split precisions: num_kb counts ring fills (3 per original k-block), num_kb1 stays in original k-blocks
+  int has_src2;
+  float acc_scale;                  // split precisions: 1 / wscale, applied to the accumulator before the bias
 };
 static_assert(sizeof(ConvTcParams) <= 896, "ConvTcLaunch::params too small");
 
@@ -86,9 +93,10 @@ template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int cta_threads
   return kAMode == A_GATHER ? 352 : (2 + epi_warps<BLOCK_N, kAMode>() + 1) * 32;
 }
 
-template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
+template <typename T, int BLOCK_N, int kAMode, bool kBRes = false, bool kSplit = false>
 __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N, kBRes>;
+  using Cfg = TcCfg<BLOCK_N, kBRes, kSplit>;
+  static_assert(!kSplit || kAMode != A_GATHER, "split precisions take their activations through TMA");
   constexpr int EPI_WARPS = epi_warps<BLOCK_N, kAMode>();
   constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING;
   extern __shared__ uint8_t smem_raw[];
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
 
   if (warp == 0 && leader) {
     if (kAMode != A_GATHER) tma_prefetch_desc(&p.tmA);
-    if (p.num_kb1 < p.num_kb) tma_prefetch_desc(&p.tmA2);
+    if (p.has_src2) tma_prefetch_desc(&p.tmA2);
     tma_prefetch_desc(&p.tmB);
     tma_prefetch_desc(&p.tmC);
     if (p.has_res) tma_prefetch_desc(&p.tmR);
@@ -164,25 +172,30 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
           w2 = ow * p.stride2;
         }
         int tap = 0, cb = 0;  // filter tap and 64-channel block of the current k-block (im2col)
+        int ko = 0, term = 0;  // split: original k-block and which of its three products this fill feeds
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], (kBRes ? 0 : Cfg::B_STAGE_BYTES) + (kAMode != A_GATHER ? A_STAGE_BYTES : 0));
-          if (kb >= p.num_kb1) {
-            const int kb2 = kb - p.num_kb1;  // fused 1x1 conv over the second activation tensor
+          if (!kSplit) ko = kb;
+          const int a_lo = kSplit && term == 1;                                   // A tile: hi, lo, hi
+          const int b_blk = kSplit ? 2 * ko + (term == 2 ? 1 : 0) : kb;           // W tile: hi, hi, lo
+          if (ko >= p.num_kb1) {
+            const int kb2 = kSplit ? 2 * (ko - p.num_kb1) + a_lo : ko - p.num_kb1;  // fused 1x1 conv over the second activation tensor
             if (p.a2_im2col)
               tma_load_im2col_4d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb2 * BLOCK_K, w2, h2, n, 0, 0);
             else
               tma_load_2d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb2 * BLOCK_K, m_tile * BLOCK_M);
           } else if (kAMode == A_TMA) {
-            tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
+            tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, (kSplit ? 2 * ko + a_lo : ko) * BLOCK_K, m_tile * BLOCK_M);
           } else if (kAMode == A_IM2COL) {
             const int r = tap / p.KW, s = tap - r * p.KW;
-            tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, cb * BLOCK_K, w0, h0, n,
+            tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, (kSplit ? 2 * cb + a_lo : cb) * BLOCK_K, w0, h0, n,
                                (uint16_t)s, (uint16_t)r);
-            if (++cb == kb_per_tap) { cb = 0; ++tap; }
+            if (!kSplit || term == 2) { if (++cb == kb_per_tap) { cb = 0; ++tap; } }
           }
           if (!kBRes)
-            tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BLOCK_N);
+            tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, b_blk * BLOCK_K, n_tile * BLOCK_N);
+          if (kSplit && ++term == 3) { term = 0; ++ko; }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -252,6 +265,44 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
           const int col0 = n_tile * BLOCK_N + col_in_tile;
+          if constexpr (kSplit) {
+            // 32 accumulator columns -> chunks j0 .. j0+3 of the group's hi box and of its lo box (same row, same chunk)
+            const int j0 = col_in_group / 8;
+            const uint32_t row_addr = smem_u32(cbuf) + row * 128;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
+              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
+              const float sc = p.acc_scale;   // a power of two: exact
+              float f[8] = {fmaf(__uint_as_float(v[j * 8 + 0]), sc, b0.x), fmaf(__uint_as_float(v[j * 8 + 1]), sc, b0.y),
+                            fmaf(__uint_as_float(v[j * 8 + 2]), sc, b0.z), fmaf(__uint_as_float(v[j * 8 + 3]), sc, b0.w),
+                            fmaf(__uint_as_float(v[j * 8 + 4]), sc, b1.x), fmaf(__uint_as_float(v[j * 8 + 5]), sc, b1.y),
+                            fmaf(__uint_as_float(v[j * 8 + 6]), sc, b1.z), fmaf(__uint_as_float(v[j * 8 + 7]), sc, b1.w)};
+              const uint32_t a_hi = row_addr + (swz_chunk<128>(j0 + j, row) << 4), a_lo = a_hi + Cfg::BOX_BYTES;
+              if (p.has_res) {
+                uint4 rh, rl;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rh.x), "=r"(rh.y), "=r"(rh.z), "=r"(rh.w) : "r"(a_hi));
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rl.x), "=r"(rl.y), "=r"(rl.z), "=r"(rl.w) : "r"(a_lo));
+                float h[8], l[8];
+                unpack8<T>(rh, h);
+                unpack8<T>(rl, l);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] += h[e] + l[e];
+              }
+              if (p.relu) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+              }
+              const uint4 oh = pack8<T>(f);
+              float h[8];
+              unpack8<T>(oh, h);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) h[e] = f[e] - h[e];   // exact: hi is f rounded to fewer bits
+              const uint4 ol = pack8<T>(h);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
+            }
+          } else {
           const int box = col_in_group / Cfg::BOX_COLS, j0 = (col_in_group % Cfg::BOX_COLS) / 8;
           const uint32_t row_addr = smem_u32(cbuf + box * Cfg::BOX_BYTES) + row * ROW_BYTES;
 #pragma unroll
@@ -277,6 +328,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
             }
             const uint4 o = pack8<T>(f);
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+          }
           }
         }
         // this warp's part of the slot is staged: make it visible to the async proxy (TMA store), then publish
@@ -304,7 +356,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
 #pragma unroll
             for (int b = 0; b < Cfg::BOXES; ++b)
               tma_load_2d(&p.tmR, &res_full_bar[l_slot], cbuf + b * Cfg::BOX_BYTES,
-                          n_tile * BLOCK_N + l_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS, m_tile * BLOCK_M);
+                          kSplit ? 2 * (n_tile * BLOCK_N + l_g * Cfg::GROUP_COLS) + b * 64 : n_tile * BLOCK_N + l_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
+                          m_tile * BLOCK_M);
           } else {
             mbar_arrive(&res_full_bar[l_slot]);
           }
@@ -318,7 +371,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
           uint8_t* cbuf = smem_c + s_slot * Cfg::GROUP_BYTES;
 #pragma unroll
           for (int b = 0; b < Cfg::BOXES; ++b)
-            tma_store_2d(&p.tmC, cbuf + b * Cfg::BOX_BYTES, n_tile * BLOCK_N + s_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
+            tma_store_2d(&p.tmC, cbuf + b * Cfg::BOX_BYTES,
+                         kSplit ? 2 * (n_tile * BLOCK_N + s_g * Cfg::GROUP_COLS) + b * 64 : n_tile * BLOCK_N + s_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
                          m_tile * BLOCK_M);
         }
         bulk_commit();
@@ -420,7 +474,7 @@ static void* driver_entry(const char* name) {
   return ptr;
 }
 static CUtensorMapDataType tmap_dtype(int precision) {
-  return precision == SEMDIFF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+  return base_precision(precision) == SEMDIFF_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
 }
 
 // 2-D 16-bit tensor [rows, cols] (cols contiguous), box = box_cols x box_rows; swizzle span = box_cols * 2 bytes; OOB -> 0
@@ -451,8 +505,9 @@ static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, con
   if (second) { s.H = s_in.H2; s.W = s_in.W2; s.cin = s_in.cin2; s.kh = s.kw = 1; s.stride = s_in.stride2; s.pad = 0; }
   static EncodeIm2colFn enc = reinterpret_cast<EncodeIm2colFn>(driver_entry("cuTensorMapEncodeIm2col"));
   if (enc == nullptr) { set_error("cuTensorMapEncodeIm2col entry point not found"); return SEMDIFF_ERR_CUDA; }
-  const cuuint64_t dims[4] = {(cuuint64_t)s.cin, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.n_img};
-  const cuuint64_t strides[3] = {(cuuint64_t)s.cin * 2, (cuuint64_t)s.W * s.cin * 2, (cuuint64_t)s.H * s.W * s.cin * 2};
+  const cuuint64_t cs = (cuuint64_t)s.cin * (is_split(precision) ? 2 : 1);   // stored 16-bit channels per pixel
+  const cuuint64_t dims[4] = {cs, (cuuint64_t)s.W, (cuuint64_t)s.H, (cuuint64_t)s.n_img};
+  const cuuint64_t strides[3] = {cs * 2, (cuuint64_t)s.W * cs * 2, (cuuint64_t)s.H * s.W * cs * 2};
   const int lower[2] = {-s.pad, -s.pad};
   const int upper[2] = {s.pad - (s.kw - 1), s.pad - (s.kh - 1)};
   const cuuint32_t estr[4] = {1, (cuuint32_t)s.stride, (cuuint32_t)s.stride, 1};
@@ -467,7 +522,7 @@ static int make_tmap_im2col(CUtensorMap* m, const void* base, int precision, con
   // Same workaround CUTLASS applies (cute/atom/copy_traits_sm90_im2col.hpp) for drivers <= 13.1: small tensors
   int drv = 0;
   cudaDriverGetVersion(&drv);
-  if (drv <= 13010 && (uint64_t)s.n_img * s.H * s.W * s.cin * 2 < 131072)
+  if (drv <= 13010 && (uint64_t)s.n_img * s.H * s.W * cs * 2 < 131072)
     reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
   return 0;
 }
@@ -496,6 +551,10 @@ static int a_mode_for(const ConvShape& s, int requested) {
 }
 
 bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma) {
+  if (is_split(precision)) {   // split precisions: TMA-fed only, whole 64-channel blocks on both sides
+    if (!use_tma || s.cin % 64 != 0 || s.cout % 64 != 0 || s.cin2 % 64 != 0) return false;
+    precision = base_precision(precision);
+  }
   if (precision != SEMDIFF_BF16 && precision != SEMDIFF_FP16) return false;
   if (s.pad_hi >= 0 && s.pad_hi != s.pad) return false;  // asymmetric padding: strip kernel or SIMT only
   if (s.cin % 8 != 0 || s.cout % 32 != 0) return false;
@@ -523,11 +582,11 @@ static int num_sms() {
   return sms[dev];
 }
 
-template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
+template <typename T, int BLOCK_N, int kAMode, bool kBRes = false, bool kSplit = false>
 static int launch_t(const ConvTcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N, kBRes>;
+  using Cfg = TcCfg<BLOCK_N, kBRes, kSplit>;
   static bool configured[MAX_DEVICES] = {};
-  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode, kBRes>;
+  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode, kBRes, kSplit>;
   const int dev = current_device();
   if (!configured[dev]) {
     SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -556,6 +615,25 @@ static int launch_n(const ConvTcParams& p, int block_n, cudaStream_t st) {
 }
 
 template <typename T>
+static int launch_split(const ConvTcParams& p, int block_n, int a_mode, cudaStream_t st) {
+  if (a_mode == A_TMA) {
+    switch (block_n) {
+      case 256: return launch_t<T, 256, A_TMA, false, true>(p, st);
+      case 128: return launch_t<T, 128, A_TMA, false, true>(p, st);
+      case 64: return launch_t<T, 64, A_TMA, false, true>(p, st);
+    }
+  } else if (a_mode == A_IM2COL) {
+    switch (block_n) {
+      case 256: return launch_t<T, 256, A_IM2COL, false, true>(p, st);
+      case 128: return launch_t<T, 128, A_IM2COL, false, true>(p, st);
+      case 64: return launch_t<T, 64, A_IM2COL, false, true>(p, st);
+    }
+  }
+  set_error("conv_tc (split): unsupported tile %d / mode %d", block_n, a_mode);
+  return SEMDIFF_ERR_UNSUPPORTED;
+}
+
+template <typename T>
 static int launch_mode(const ConvTcParams& p, int block_n, int a_mode, cudaStream_t st) {
   switch (a_mode) {
     case A_TMA: return launch_n<T, A_TMA>(p, block_n, st);
@@ -580,33 +658,36 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   ConvTcParams& p = *reinterpret_cast<ConvTcParams*>(L->params);
   memset(&p, 0, sizeof(p));
   const int a_mode = a_mode_for(s, use_tma ? SEMDIFF_CONV_TC_TMA : SEMDIFF_CONV_TC_GATHER);
+  const bool split = is_split(precision);
+  const int kmul = split ? 2 : 1;    // stored 16-bit columns per logical channel
   p.M = (int)s.M();
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K;
+  p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K * (split ? 3 : 1);
   const int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
   if (block_n == 0) { set_error("conv_tc: cout %d not a multiple of 32", s.cout); return SEMDIFF_ERR_UNSUPPORTED; }
   p.in = in; p.bias = bias; p.has_res = res != nullptr;
   p.H = s.H; p.W = s.W; p.Cin = s.cin; p.OH = s.OH(); p.OW = s.OW(); p.Cout = s.cout;
   p.KH = s.kh; p.KW = s.kw; p.stride = s.stride; p.pad = s.pad; p.relu = s.relu;
-  p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K;
   p.n_tiles = s.cout / block_n;
+  p.acc_scale = split && s.wscale > 0.f ? 1.f / s.wscale : 1.f;
   p.cpt = s.cin / 8;
   p.taps = s.kh * s.kw;
   const uint32_t box_cols = block_n < 64 ? block_n : 64;
-  int rc = make_tmap_2d(&p.tmB, w, precision, (uint64_t)s.cout, (uint64_t)s.K(), BLOCK_K, (uint32_t)block_n);
-  if (rc == 0 && a_mode == A_TMA) rc = make_tmap_2d(&p.tmA, in, precision, (uint64_t)p.M, (uint64_t)s.cin, BLOCK_K, BLOCK_M);
+  int rc = make_tmap_2d(&p.tmB, w, precision, (uint64_t)s.cout, (uint64_t)s.K() * kmul, BLOCK_K, (uint32_t)block_n);
+  if (rc == 0 && a_mode == A_TMA) rc = make_tmap_2d(&p.tmA, in, precision, (uint64_t)p.M, (uint64_t)s.cin * kmul, BLOCK_K, BLOCK_M);
   if (rc == 0 && a_mode == A_IM2COL) rc = make_tmap_im2col(&p.tmA, in, precision, s, false);
-  p.num_kb1 = p.num_kb;
+  p.num_kb1 = (s.K() + BLOCK_K - 1) / BLOCK_K;   // original k-blocks (the producer counts in these)
   p.stride2 = 1;
   if (rc == 0 && s.cin2 != 0) {
     p.num_kb1 = s.K1() / BLOCK_K;
+    p.has_src2 = 1;
     p.stride2 = s.stride2;
     p.a2_im2col = s.stride2 != 1;
     rc = p.a2_im2col ? make_tmap_im2col(&p.tmA2, q.in2, precision, s, true)
-                     : make_tmap_2d(&p.tmA2, q.in2, precision, (uint64_t)p.M, (uint64_t)s.cin2, BLOCK_K, BLOCK_M);
+                     : make_tmap_2d(&p.tmA2, q.in2, precision, (uint64_t)p.M, (uint64_t)s.cin2 * kmul, BLOCK_K, BLOCK_M);
   }
-  if (rc == 0) rc = make_tmap_2d(&p.tmC, out, precision, (uint64_t)p.M, (uint64_t)s.cout, box_cols, BLOCK_M);
-  if (rc == 0 && res != nullptr) rc = make_tmap_2d(&p.tmR, res, precision, (uint64_t)p.M, (uint64_t)s.cout, box_cols, BLOCK_M);
+  if (rc == 0) rc = make_tmap_2d(&p.tmC, out, precision, (uint64_t)p.M, (uint64_t)s.cout * kmul, box_cols, BLOCK_M);
+  if (rc == 0 && res != nullptr) rc = make_tmap_2d(&p.tmR, res, precision, (uint64_t)p.M, (uint64_t)s.cout * kmul, box_cols, BLOCK_M);
   if (rc != 0) return rc;
   L->block_n = block_n;
   L->a_mode = a_mode;
@@ -618,8 +699,14 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t st) {
   if (L->a_mode > 200) return conv_chain_launch(L, st);
   if (L->a_mode > 100) return conv_strip_launch(L, st);
   const ConvTcParams& p = *reinterpret_cast<const ConvTcParams*>(L->params);
-  if (L->precision == SEMDIFF_BF16) return launch_mode<__nv_bfloat16>(p, L->block_n, L->a_mode, st);
-  return launch_mode<__half>(p, L->block_n, L->a_mode, st);
+  switch (L->precision) {
+    case SEMDIFF_BF16: return launch_mode<__nv_bfloat16>(p, L->block_n, L->a_mode, st);
+    case SEMDIFF_FP16: return launch_mode<__half>(p, L->block_n, L->a_mode, st);
+    case SEMDIFF_FP16X3: return launch_split<__half>(p, L->block_n, L->a_mode, st);
+    case SEMDIFF_BF16X3: return launch_split<__nv_bfloat16>(p, L->block_n, L->a_mode, st);
+  }
+  set_error("conv_tc: bad precision %d", L->precision);
+  return SEMDIFF_ERR_ARG;
 }
 
 int launch_conv_tc(const ConvPtrs& q, const ConvShape& s, int precision, bool use_tma, cudaStream_t st) {

@@ -31,6 +31,24 @@ template <typename T> __device__ __forceinline__ void load8_stream(const T* p, f
   }
 }
 
+// 8 logical channels starting at channel c (multiple of 8) of the pixel whose stored channel vector starts at px.
+// Split precisions store a pixel as blocks of [64 hi | 64 lo]; the value is hi + lo.
+template <typename T, bool kSplit> __device__ __forceinline__ void load8_px(const T* px, int c, float (&f)[8]) {
+  if constexpr (kSplit) {
+    const T* q = px + (c >> 6) * 128 + (c & 63);
+    float l[8];
+    unpack8<T>(*reinterpret_cast<const uint4*>(q), f);
+    unpack8<T>(*reinterpret_cast<const uint4*>(q + 64), l);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += l[k];
+  } else if constexpr (sizeof(T) == 2) {
+    unpack8<T>(*reinterpret_cast<const uint4*>(px + c), f);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] = Elem<T>::to_f(px[c + k]);
+  }
+}
+
 __device__ __forceinline__ float block_reduce_fixed(float v, float* smem) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -105,10 +123,66 @@ __global__ void __launch_bounds__(DIST_THREADS) distance_kernel(const T* __restr
   if (threadIdx.x == 0) partial[(int64_t)pair * SEMDIFF_MAX_PARTS + part] = t;
 }
 
+// Split precisions: logical 8-channel chunk i of an image lives at stored offset (i / 8) * 128 + (i % 8) * 8 (hi) and 64
+// elements further (lo).  d = (ah - bh) + (al - bl): the hi difference is exact in fp32 for nearby values, so the
+// difference keeps the full hi + lo resolution even when a and b agree in their leading bits (SR ~ GT pairs).
+template <typename T, bool kRegW>
+__global__ void __launch_bounds__(DIST_THREADS) distance_split_kernel(const T* __restrict__ act, int n_pairs, int64_t elems,
+                                                                      int C, const float* __restrict__ w,
+                                                                      int64_t chunks_per_part, float* __restrict__ partial) {
+  pdl_trigger();
+  pdl_wait();
+  __shared__ float red[DIST_THREADS / 32];
+  const int pair = blockIdx.y, part = blockIdx.x;
+  const T* a = act + (int64_t)pair * elems * 2;
+  const T* b = act + (int64_t)(pair + n_pairs) * elems * 2;
+  const int64_t total_chunks = elems / 8;
+  const int64_t c_begin = (int64_t)part * chunks_per_part;
+  int64_t c_end = c_begin + chunks_per_part;
+  if (c_end > total_chunks) c_end = total_chunks;
+  float wr[8];
+  if constexpr (kRegW) {
+    const int c0 = (int)(((c_begin + threadIdx.x) * 8) % C);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[k] = __ldg(w + c0 + k);
+  }
+  float acc = 0.f;
+  auto accumulate = [&](int64_t i, const uint4& ah, const uint4& al, const uint4& bh, const uint4& bl) {
+    float fah[8], fal[8], fbh[8], fbl[8];
+    unpack8<T>(ah, fah); unpack8<T>(al, fal); unpack8<T>(bh, fbh); unpack8<T>(bl, fbl);
+    if constexpr (!kRegW) {
+      const int c0 = (int)((i * 8) % C);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wr[k] = __ldg(w + c0 + k);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = (fah[k] - fbh[k]) + (fal[k] - fbl[k]); acc = fmaf(wr[k], d * d, acc); }
+  };
+  int64_t i = c_begin + threadIdx.x;
+  for (; i + DIST_THREADS < c_end; i += 2 * DIST_THREADS) {
+    uint4 q[2][4];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int64_t j = i + u * DIST_THREADS;
+      const int64_t off = (j >> 3) * 128 + (j & 7) * 8;
+      q[u][0] = ld_nc_u4(a + off); q[u][1] = ld_nc_u4(a + off + 64);
+      q[u][2] = ld_nc_u4(b + off); q[u][3] = ld_nc_u4(b + off + 64);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) accumulate(i + u * DIST_THREADS, q[u][0], q[u][1], q[u][2], q[u][3]);
+  }
+  for (; i < c_end; i += DIST_THREADS) {
+    const int64_t off = (i >> 3) * 128 + (i & 7) * 8;
+    accumulate(i, ld_nc_u4(a + off), ld_nc_u4(a + off + 64), ld_nc_u4(b + off), ld_nc_u4(b + off + 64));
+  }
+  const float t = block_reduce_fixed(acc, red);
+  if (threadIdx.x == 0) partial[(int64_t)pair * SEMDIFF_MAX_PARTS + part] = t;
+}
+
 // Optional LPIPS-style variant (default OFF; the reference does not normalise): each
 // pixel's channel vector is scaled to unit L2 norm (eps 1e-10) before the difference.  One warp per
 // pixel, two passes over the pixel's channels (second pass hits L1).  grid = (n_parts, n_pairs).
-template <typename T>
+template <typename T, bool kSplit>
 __global__ void __launch_bounds__(DIST_THREADS) distance_norm_kernel(const T* __restrict__ act, int n_pairs, int hw,
                                                                      int C, const float* __restrict__ w,
                                                                      int pix_per_part, float* __restrict__ partial) {
@@ -117,22 +191,20 @@ __global__ void __launch_bounds__(DIST_THREADS) distance_norm_kernel(const T* __
   __shared__ float red[DIST_THREADS / 32];
   const int pair = blockIdx.y, part = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const T* a = act + (int64_t)pair * hw * C;
-  const T* b = act + (int64_t)(pair + n_pairs) * hw * C;
+  const int CS = kSplit ? 2 * C : C;   // stored elements per pixel
+  const T* a = act + (int64_t)pair * hw * CS;
+  const T* b = act + (int64_t)(pair + n_pairs) * hw * CS;
   int p_end = (part + 1) * pix_per_part;
   if (p_end > hw) p_end = hw;
   float acc = 0.f;
   for (int p = part * pix_per_part + warp; p < p_end; p += DIST_THREADS / 32) {
-    const T* pa = a + (int64_t)p * C;
-    const T* pb = b + (int64_t)p * C;
+    const T* pa = a + (int64_t)p * CS;
+    const T* pb = b + (int64_t)p * CS;
     float sa = 0.f, sb = 0.f;
     for (int c = lane * 8; c < C; c += 256) {
       float fa[8], fb[8];
-      if constexpr (sizeof(T) == 2) { unpack8<T>(*reinterpret_cast<const uint4*>(pa + c), fa); unpack8<T>(*reinterpret_cast<const uint4*>(pb + c), fb); }
-      else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { fa[k] = Elem<T>::to_f(pa[c + k]); fb[k] = Elem<T>::to_f(pb[c + k]); }
-      }
+      load8_px<T, kSplit>(pa, c, fa);
+      load8_px<T, kSplit>(pb, c, fb);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { sa = fmaf(fa[k], fa[k], sa); sb = fmaf(fb[k], fb[k], sb); }
     }
@@ -141,11 +213,8 @@ __global__ void __launch_bounds__(DIST_THREADS) distance_norm_kernel(const T* __
     const float ia = 1.f / (sqrtf(sa) + 1e-10f), ib = 1.f / (sqrtf(sb) + 1e-10f);
     for (int c = lane * 8; c < C; c += 256) {
       float fa[8], fb[8];
-      if constexpr (sizeof(T) == 2) { unpack8<T>(*reinterpret_cast<const uint4*>(pa + c), fa); unpack8<T>(*reinterpret_cast<const uint4*>(pb + c), fb); }
-      else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { fa[k] = Elem<T>::to_f(pa[c + k]); fb[k] = Elem<T>::to_f(pb[c + k]); }
-      }
+      load8_px<T, kSplit>(pa, c, fa);
+      load8_px<T, kSplit>(pb, c, fb);
 #pragma unroll
       for (int k = 0; k < 8; ++k) { const float d = fa[k] * ia - fb[k] * ib; acc = fmaf(__ldg(w + c + k), d * d, acc); }
     }
@@ -157,7 +226,7 @@ __global__ void __launch_bounds__(DIST_THREADS) distance_norm_kernel(const T* __
 // Per-channel spatial mean of (a-b)^2: chan_mean[pair][c].  Feeds d(score)/d(w_layers) for callers that
 // train the head (sweep script :55-69).  grid = (C/8/32 .. , n_pairs): a thread owns 8 channels and
 // walks the pixels in order (fixed order -> deterministic).
-template <typename T>
+template <typename T, bool kSplit>
 __global__ void __launch_bounds__(128) chan_mean_kernel(const T* __restrict__ act, int n_pairs, int hw, int C,
                                                         float* __restrict__ chan_mean, int chan_stride) {
   pdl_trigger();
@@ -165,16 +234,14 @@ __global__ void __launch_bounds__(128) chan_mean_kernel(const T* __restrict__ ac
   const int pair = blockIdx.y;
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   if (c8 * 8 >= C) return;
-  const T* a = act + (int64_t)pair * hw * C + c8 * 8;
-  const T* b = act + (int64_t)(pair + n_pairs) * hw * C + c8 * 8;
+  const int CS = kSplit ? 2 * C : C;   // stored elements per pixel
+  const T* a = act + (int64_t)pair * hw * CS;
+  const T* b = act + (int64_t)(pair + n_pairs) * hw * CS;
   float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int p = 0; p < hw; ++p) {
     float fa[8], fb[8];
-    if constexpr (sizeof(T) == 2) { unpack8<T>(*reinterpret_cast<const uint4*>(a + (int64_t)p * C), fa); unpack8<T>(*reinterpret_cast<const uint4*>(b + (int64_t)p * C), fb); }
-    else {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { fa[k] = a[(int64_t)p * C + k]; fb[k] = b[(int64_t)p * C + k]; }
-    }
+    load8_px<T, kSplit>(a + (int64_t)p * CS, c8 * 8, fa);
+    load8_px<T, kSplit>(b + (int64_t)p * CS, c8 * 8, fb);
 #pragma unroll
     for (int k = 0; k < 8; ++k) { const float d = fa[k] - fb[k]; acc[k] = fmaf(d, d, acc[k]); }
   }
@@ -183,14 +250,21 @@ __global__ void __launch_bounds__(128) chan_mean_kernel(const T* __restrict__ ac
   for (int k = 0; k < 8; ++k) chan_mean[(int64_t)pair * chan_stride + c8 * 8 + k] = acc[k] * inv;
 }
 
-template <typename T>
+template <typename T, bool kSplit = false>
 static int distance_t(const void* act, int n_pairs, int hw, int c, const float* w, int normalize, float* partial,
                       float* chan_mean, int chan_stride, cudaStream_t st) {
   const int parts = distance_parts(hw, c);
   dim3 grid(parts, n_pairs);
   if (normalize) {
     const int ppp = (hw + parts - 1) / parts;
-    launch_pdl(distance_norm_kernel<T>, dim3(grid), dim3(DIST_THREADS), 0, st, (const T*)act, n_pairs, hw, c, w, ppp, partial);
+    launch_pdl(distance_norm_kernel<T, kSplit>, dim3(grid), dim3(DIST_THREADS), 0, st, (const T*)act, n_pairs, hw, c, w, ppp, partial);
+  } else if constexpr (kSplit) {
+    const int64_t elems = (int64_t)hw * c;
+    const int64_t cpp = (elems / 8 + parts - 1) / parts;
+    if ((8 * DIST_THREADS) % c == 0)
+      launch_pdl(distance_split_kernel<T, true>, dim3(grid), dim3(DIST_THREADS), 0, st, (const T*)act, n_pairs, elems, c, w, cpp, partial);
+    else
+      launch_pdl(distance_split_kernel<T, false>, dim3(grid), dim3(DIST_THREADS), 0, st, (const T*)act, n_pairs, elems, c, w, cpp, partial);
   } else {
     const int64_t elems = (int64_t)hw * c;
     const int64_t cpp = (elems / 8 + parts - 1) / parts;
@@ -202,7 +276,7 @@ static int distance_t(const void* act, int n_pairs, int hw, int c, const float* 
   SEMDIFF_CUDA_OK(cudaGetLastError());
   if (chan_mean != nullptr) {
     dim3 g2((c / 8 + 127) / 128, n_pairs);
-    launch_pdl(chan_mean_kernel<T>, dim3(g2), dim3(128), 0, st, (const T*)act, n_pairs, hw, c, chan_mean, chan_stride);
+    launch_pdl(chan_mean_kernel<T, kSplit>, dim3(g2), dim3(128), 0, st, (const T*)act, n_pairs, hw, c, chan_mean, chan_stride);
     SEMDIFF_CUDA_OK(cudaGetLastError());
   }
   return 0;
@@ -212,7 +286,10 @@ int launch_distance(const void* act, int n_pairs, int hw, int c, const float* w,
                     float* chan_mean, int chan_stride, int precision, cudaStream_t st) {
   if (n_pairs <= 0 || hw <= 0 || c <= 0 || c % 8 != 0) { set_error("distance: need c %% 8 == 0, non-empty"); return SEMDIFF_ERR_ARG; }
   if (n_pairs > 65535) { set_error("distance: n_pairs > 65535 per launch"); return SEMDIFF_ERR_ARG; }
+  if (is_split(precision) && c % 64 != 0) { set_error("distance: split precisions need c %% 64 == 0"); return SEMDIFF_ERR_ARG; }
   switch (precision) {
+    case SEMDIFF_FP16X3: return distance_t<__half, true>(act, n_pairs, hw, c, w, normalize, partial, chan_mean, chan_stride, st);
+    case SEMDIFF_BF16X3: return distance_t<__nv_bfloat16, true>(act, n_pairs, hw, c, w, normalize, partial, chan_mean, chan_stride, st);
     case SEMDIFF_BF16: return distance_t<__nv_bfloat16>(act, n_pairs, hw, c, w, normalize, partial, chan_mean, chan_stride, st);
     case SEMDIFF_FP16: return distance_t<__half>(act, n_pairs, hw, c, w, normalize, partial, chan_mean, chan_stride, st);
     case SEMDIFF_FP32: return distance_t<float>(act, n_pairs, hw, c, w, normalize, partial, chan_mean, chan_stride, st);
@@ -243,7 +320,7 @@ __global__ void __launch_bounds__(128) head_kernel(const float* __restrict__ par
   }
   const float v = n_taps == 1 ? total : total / (float)n_taps;
   if (pre != nullptr) pre[p] = v;
-  out[p] = fmaxf(v, 0.f);
+  out[p] = v > 0.f ? v : (v != v ? v : 0.f);   // torch.relu propagates NaN (fmaxf would turn it into a perfect score)
 }
 
 int launch_head(const float* partials, int n_taps, int n_pairs, const int* n_parts, const int* hw, const float* head_b,

@@ -50,7 +50,9 @@ __global__ void __launch_bounds__(256) pack_kernel(const TIn* __restrict__ gt, c
 // 49 x 8 a channel-padded 7x7 window would need.  One thread per (img, i, q, j): 6 float2 reads, 32 bytes written.
 // The same kernel serves SEMDIFF_INPUT_S2D_ROW2 (3x3 stride-2 pad-1 stems, CLIP): window of 2 s2d pixels starting one
 // to the left, one padding row on top (i -> y = 2*(i-1)+dy), slots j = 2, 3 zero (so the row is still 64 wide).
-template <typename T, typename TIn>
+// kSplit (split precisions): the pixel row is 128 stored values, [64 hi | 64 lo]; slot j writes 16 hi values at j*16 and
+// the 16 lo values (x - hi, rounded) at 64 + j*16.
+template <typename T, typename TIn, bool kSplit = false>
 __global__ void __launch_bounds__(256) pack_s2d_kernel(const TIn* __restrict__ gt, const TIn* __restrict__ sr,
                                                        int n_pairs, int img0, int H, int W, T* __restrict__ out,
                                                        int j_real, int off) {
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const TIn* __restrict__ g
   const int img = img0 + blockIdx.y;
   const int plane = H * W;
   const TIn* src = img < n_pairs ? gt + (int64_t)img * 3 * plane : sr + (int64_t)(img - n_pairs) * 3 * plane;
-  T* out_img = out + (int64_t)blockIdx.y * per_img * 16;
+  T* out_img = out + (int64_t)blockIdx.y * per_img * (kSplit ? 32 : 16);
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < per_img; t += gridDim.x * blockDim.x) {
     const int j = t & 3;
     const int r = t >> 2;
@@ -80,6 +82,22 @@ __global__ void __launch_bounds__(256) pack_s2d_kernel(const TIn* __restrict__ g
           load2<TIn>(src + ci * plane + y * W + x0, f[(dy * 2 + 0) * 3 + ci], f[(dy * 2 + 1) * 3 + ci]);
         }
       }
+    }
+    if constexpr (kSplit) {
+      T* dst = out_img + (int64_t)r * 128 + j * 16;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float v[8], h[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = f[half * 8 + k];
+        const uint4 qh = pack8<T>(v);
+        unpack8<T>(qh, h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) h[k] = v[k] - h[k];
+        reinterpret_cast<uint4*>(dst)[half] = qh;
+        reinterpret_cast<uint4*>(dst + 64)[half] = pack8<T>(h);
+      }
+      continue;
     }
     T* dst = out_img + (int64_t)t * 16;
     if constexpr (sizeof(T) == 2) {
@@ -249,17 +267,117 @@ __global__ void __launch_bounds__(256) avgpool_kernel(const T* __restrict__ in, 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// split precisions: a pixel's C logical channels are stored as C/64 blocks of [64 hi | 64 lo]
+// ---------------------------------------------------------------------------------------------
+// stored offset of the hi half of the 8-channel group c8 (the lo half is 64 elements further)
+__device__ __forceinline__ int split_off(int c8) { return (c8 >> 3) * 128 + (c8 & 7) * 8; }
+
+// max of (hi, lo) pairs: hi = round(x) is monotone in x, so the order of x is the lexicographic order of (hi, lo)
+template <typename T>
+__global__ void __launch_bounds__(256) maxpool_split_kernel(const T* __restrict__ in, T* __restrict__ out, int H, int W, int C,
+                                                            int OH, int OW) {
+  pdl_trigger();
+  pdl_wait();
+  const int cv = C / 8;
+  const int per_img = OH * OW * cv;
+  const T* img_in = in + (int64_t)blockIdx.y * H * W * C * 2;
+  T* img_out = out + (int64_t)blockIdx.y * OH * OW * C * 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_img; i += gridDim.x * blockDim.x) {
+    const int c8 = i % cv;
+    const int p = i / cv;
+    const int oh = p / OW, ow = p - oh * OW;
+    const int so = split_off(c8);
+    float mh[8], ml[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { mh[k] = -INFINITY; ml[k] = 0.f; }
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int ih = oh * 2 - 1 + r;
+      if (ih < 0 || ih >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int iw = ow * 2 - 1 + s;
+        if (iw < 0 || iw >= W) continue;
+        const T* px = img_in + ((int64_t)ih * W + iw) * C * 2 + so;
+        float h[8], l[8];
+        unpack8<T>(*reinterpret_cast<const uint4*>(px), h);
+        unpack8<T>(*reinterpret_cast<const uint4*>(px + 64), l);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const bool better = h[k] > mh[k] || (h[k] == mh[k] && l[k] > ml[k]);
+          mh[k] = better ? h[k] : mh[k];
+          ml[k] = better ? l[k] : ml[k];
+        }
+      }
+    }
+    T* dst = img_out + (int64_t)p * C * 2 + so;
+    *reinterpret_cast<uint4*>(dst) = pack8<T>(mh);
+    *reinterpret_cast<uint4*>(dst + 64) = pack8<T>(ml);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) avgpool_split_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int H,
+                                                            int W, int C, int win) {
+  pdl_trigger();
+  pdl_wait();
+  const int cv = C / 8, OH = H / win, OW = W / win;
+  const int64_t total = (int64_t)n_img * OH * OW * cv;
+  const float inv = 1.f / (float)(win * win);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    int64_t p = i / cv;
+    const int ow = (int)(p % OW); p /= OW;
+    const int oh = (int)(p % OH);
+    const int n = (int)(p / OH);
+    const int so = split_off(c8);
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < win; ++r)
+      for (int s = 0; s < win; ++s) {
+        const T* px = in + (((int64_t)n * H + oh * win + r) * W + ow * win + s) * C * 2 + so;
+        float h[8], l[8];
+        unpack8<T>(*reinterpret_cast<const uint4*>(px), h);
+        unpack8<T>(*reinterpret_cast<const uint4*>(px + 64), l);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a[k] += h[k] + l[k];
+      }
+    float h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] *= inv;
+    const uint4 qh = pack8<T>(a);
+    unpack8<T>(qh, h);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) h[k] = a[k] - h[k];
+    T* dst = out + (((int64_t)n * OH + oh) * OW + ow) * C * 2 + so;
+    *reinterpret_cast<uint4*>(dst) = qh;
+    *reinterpret_cast<uint4*>(dst + 64) = pack8<T>(h);
+  }
+}
+
 static int grid_for(int64_t total, int block) {
   int64_t g = (total + block - 1) / block;
   const int64_t cap = 148 * 32;  // a few waves of 256-thread CTAs over 148 SMs; grid-stride covers the rest
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
-template <typename T, typename TIn>
+template <typename T, typename TIn, bool kSplit = false>
 static int pack_t(const void* gt_, const void* sr_, int n_pairs, int img0, int n_imgs, int H, int W, void* out,
                   int layout, cudaStream_t st) {
   const TIn* gt = (const TIn*)gt_;
   const TIn* sr = (const TIn*)sr_;
+  if constexpr (kSplit) {
+    if (layout != SEMDIFF_INPUT_S2D_ROW4 && layout != SEMDIFF_INPUT_S2D_ROW2) {
+      set_error("pack: the split precisions take the row-window stem layouts only (even image sizes)");
+      return SEMDIFF_ERR_UNSUPPORTED;
+    }
+    const bool row4 = layout == SEMDIFF_INPUT_S2D_ROW4;
+    const int per_img = (H / 2 + (row4 ? 3 : 1)) * (W / 2) * 4;
+    dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)n_imgs);
+    launch_pdl(pack_s2d_kernel<T, TIn, true>, dim3(grid), dim3(256), 0, st, gt, sr, n_pairs, img0, H, W, (T*)out, row4 ? 4 : 2, row4 ? 2 : 1);
+    SEMDIFF_CUDA_OK(cudaGetLastError());
+    return 0;
+  } else
   if (layout == SEMDIFF_INPUT_S2D16) {
     const int per_img = (H / 2) * (W / 2);
     dim3 grid((unsigned)std::min((per_img + 255) / 256, 64), (unsigned)n_imgs);
@@ -276,13 +394,13 @@ static int pack_t(const void* gt_, const void* sr_, int n_pairs, int img0, int n
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
-template <typename T>
+template <typename T, bool kSplit = false>
 static int pack_in(const void* gt, const void* sr, int n_pairs, int img0, int n_imgs, int H, int W, void* out, int layout,
                    int in_precision, cudaStream_t st) {
   switch (in_precision) {
-    case SEMDIFF_FP32: return pack_t<T, float>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
-    case SEMDIFF_BF16: return pack_t<T, __nv_bfloat16>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
-    case SEMDIFF_FP16: return pack_t<T, __half>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+    case SEMDIFF_FP32: return pack_t<T, float, kSplit>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+    case SEMDIFF_BF16: return pack_t<T, __nv_bfloat16, kSplit>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
+    case SEMDIFF_FP16: return pack_t<T, __half, kSplit>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, st);
   }
   set_error("pack: bad input precision %d", in_precision);
   return SEMDIFF_ERR_ARG;
@@ -299,23 +417,30 @@ int launch_pack(const void* gt, const void* sr, int in_precision, int n_pairs, i
     case SEMDIFF_BF16: return pack_in<__nv_bfloat16>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, in_precision, st);
     case SEMDIFF_FP16: return pack_in<__half>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, in_precision, st);
     case SEMDIFF_FP32: return pack_in<float>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, in_precision, st);
+    case SEMDIFF_FP16X3: return pack_in<__half, true>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, in_precision, st);
+    case SEMDIFF_BF16X3: return pack_in<__nv_bfloat16, true>(gt, sr, n_pairs, img0, n_imgs, H, W, out, layout, in_precision, st);
   }
   set_error("pack: bad precision %d", precision);
   return SEMDIFF_ERR_ARG;
 }
 
-template <typename T>
+template <typename T, bool kSplit = false>
 static int maxpool_t(const void* in, void* out, int n, int H, int W, int C, cudaStream_t st) {
   const int OH = (H + 2 - 3) / 2 + 1, OW = (W + 2 - 3) / 2 + 1;
   const int per_img = OH * OW * (C / 8);
   dim3 grid((unsigned)std::min((per_img + 255) / 256, 128), (unsigned)n);
+  if constexpr (kSplit) launch_pdl(maxpool_split_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)in, (T*)out, H, W, C, OH, OW);
+  else
   launch_pdl(maxpool_kernel<T>, dim3(grid), dim3(256), 0, st, (const T*)in, (T*)out, H, W, C, OH, OW);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
 }
 int launch_maxpool3x3s2(const void* in, void* out, int n, int H, int W, int C, int precision, cudaStream_t st) {
   if (C % 8 != 0 || n <= 0) { set_error("maxpool: C %% 8 != 0 or empty"); return SEMDIFF_ERR_ARG; }
+  if (is_split(precision) && C % 64 != 0) { set_error("maxpool: split precisions need C %% 64 == 0"); return SEMDIFF_ERR_ARG; }
   switch (precision) {
+    case SEMDIFF_FP16X3: return maxpool_t<__half, true>(in, out, n, H, W, C, st);
+    case SEMDIFF_BF16X3: return maxpool_t<__nv_bfloat16, true>(in, out, n, H, W, C, st);
     case SEMDIFF_BF16: return maxpool_t<__nv_bfloat16>(in, out, n, H, W, C, st);
     case SEMDIFF_FP16: return maxpool_t<__half>(in, out, n, H, W, C, st);
     case SEMDIFF_FP32: return maxpool_t<float>(in, out, n, H, W, C, st);
@@ -324,9 +449,11 @@ int launch_maxpool3x3s2(const void* in, void* out, int n, int H, int W, int C, i
   return SEMDIFF_ERR_ARG;
 }
 
-template <typename T>
+template <typename T, bool kSplit = false>
 static int avgpool_t(const void* in, void* out, int n, int H, int W, int C, int win, cudaStream_t st) {
   const int64_t total = (int64_t)n * (H / win) * (W / win) * (C / 8);
+  if constexpr (kSplit) launch_pdl(avgpool_split_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T*)in, (T*)out, n, H, W, C, win);
+  else
   launch_pdl(avgpool_kernel<T>, dim3(grid_for(total, 256)), dim3(256), 0, st, (const T*)in, (T*)out, n, H, W, C, win);
   SEMDIFF_CUDA_OK(cudaGetLastError());
   return 0;
@@ -336,7 +463,10 @@ int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int wi
     set_error("avgpool: need C %% 8 == 0 and H, W >= window");
     return SEMDIFF_ERR_ARG;
   }
+  if (is_split(precision) && C % 64 != 0) { set_error("avgpool: split precisions need C %% 64 == 0"); return SEMDIFF_ERR_ARG; }
   switch (precision) {
+    case SEMDIFF_FP16X3: return avgpool_t<__half, true>(in, out, n, H, W, C, win, st);
+    case SEMDIFF_BF16X3: return avgpool_t<__nv_bfloat16, true>(in, out, n, H, W, C, win, st);
     case SEMDIFF_BF16: return avgpool_t<__nv_bfloat16>(in, out, n, H, W, C, win, st);
     case SEMDIFF_FP16: return avgpool_t<__half>(in, out, n, H, W, C, win, st);
     case SEMDIFF_FP32: return avgpool_t<float>(in, out, n, H, W, C, win, st);

@@ -14,6 +14,7 @@ struct ConvShape {
   int n_img, H, W, cin, cout, kh, kw, stride, pad, relu;
   int cin2 = 0, stride2 = 1, H2 = 0, W2 = 0;
   int pad_hi = -1;  // padding after the last row / column when it differs from `pad` (-1: symmetric)
+  float wscale = 1.f;  // split precisions: the weights were multiplied by this power of two; the epilogue divides it out
   int pad_after() const { return pad_hi < 0 ? pad : pad_hi; }
   int OH() const { return (H + pad + pad_after() - kh) / stride + 1; }
   int OW() const { return (W + pad + pad_after() - kw) / stride + 1; }
@@ -38,7 +39,12 @@ inline cudaError_t launch_pdl(void (*kern)(P...), dim3 grid, dim3 block, size_t 
   return cudaLaunchKernelEx(&cfg, kern, static_cast<A&&>(args)...);
 }
 
-inline size_t elem_bytes(int precision) { return precision == SEMDIFF_FP32 ? 4 : 2; }
+// split precisions (SEMDIFF_FP16X3 / BF16X3): a logical element is a (hi, lo) pair of 16-bit numbers
+inline bool is_split(int precision) { return precision == SEMDIFF_FP16X3 || precision == SEMDIFF_BF16X3; }
+inline int base_precision(int precision) {
+  return precision == SEMDIFF_FP16X3 ? SEMDIFF_FP16 : (precision == SEMDIFF_BF16X3 ? SEMDIFF_BF16 : precision);
+}
+inline size_t elem_bytes(int precision) { return precision == SEMDIFF_FP32 || is_split(precision) ? 4 : 2; }
 
 // each returns 0 / negative error code; all asynchronous on `stream`
 // images [img0, img0 + n_imgs) of the stacked (GT..., SR...) batch -> out[0 .. n_imgs)

@@ -175,6 +175,7 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
 }
 
 static int choose_impl(const semdiff_plan* P, const ConvShape& cs) {
+  if (is_split(P->precision)) return conv_tc_supported(cs, P->precision, true) ? SEMDIFF_CONV_TC_TMA : -1;   // tensor cores or nothing
   if (P->precision == SEMDIFF_FP32 || P->conv_impl == SEMDIFF_CONV_SIMT) return SEMDIFF_CONV_SIMT;
   if (P->conv_impl != SEMDIFF_CONV_TC_GATHER && cs.cin < 64 && conv_strip_supported(cs, P->precision)) return SEMDIFF_CONV_TC_TMA;
   if ((P->conv_impl != SEMDIFF_CONV_TC_GATHER || cs.cin2 != 0) && conv_tc_supported(cs, P->precision, true))
@@ -187,6 +188,7 @@ static ConvShape conv_shape(const semdiff_op& op, const BufShape& in, const BufS
   ConvShape cs;
   cs.n_img = n_img; cs.H = in.h; cs.W = in.w; cs.cin = op.cin; cs.cout = op.cout; cs.kh = op.kh; cs.kw = op.kw;
   cs.stride = op.stride; cs.pad = op.pad; cs.relu = op.relu; cs.pad_hi = op.pad_hi;
+  cs.wscale = op.wscale > 0.f ? op.wscale : 1.f;
   if (op.src2 >= 0) { cs.cin2 = op.cin2; cs.stride2 = op.stride2 < 1 ? 1 : op.stride2; cs.H2 = in2.h; cs.W2 = in2.w; }
   return cs;
 }
@@ -217,6 +219,11 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
     if (in_head && i + 1 == P->head_ops) { set_error("the last head op must be a pooling op"); return SEMDIFF_ERR_UNSUPPORTED; }
     const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], in_head ? chunk : 2 * pairs);
     const int impl = choose_impl(P, cs);
+    if (impl < 0) {
+      set_error("op %d: conv %dx%d cin=%d cout=%d stride=%d has no split-precision kernel (needs whole 64-channel blocks)", i, op.kh, op.kw,
+                op.cin, op.cout, op.stride);
+      return SEMDIFF_ERR_UNSUPPORTED;
+    }
     S->impl[i] = impl;
     const bool next_max = i + 1 < n_ops && P->ops[i + 1].kind == SEMDIFF_OP_MAXPOOL3S2 && conv_strip_pool_supported(cs, P->precision);
     const bool next_avg = i + 1 < n_ops && P->ops[i + 1].kind == SEMDIFF_OP_AVGPOOL && P->ops[i + 1].stride == 2 &&
@@ -293,7 +300,11 @@ const char* semdiff_version(void) { return "semdiff_b200 0.1 sm_100a"; }
 int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, int32_t precision, int32_t input_layout,
                         int32_t head_ops, semdiff_plan** out) {
   if (ops == nullptr || out == nullptr || n_ops <= 0 || n_bufs < 2) { set_error("plan_create: bad arguments"); return SEMDIFF_ERR_ARG; }
-  if (precision < SEMDIFF_BF16 || precision > SEMDIFF_FP32) { set_error("plan_create: bad precision %d", precision); return SEMDIFF_ERR_ARG; }
+  if (precision < SEMDIFF_BF16 || precision > SEMDIFF_BF16X3) { set_error("plan_create: bad precision %d", precision); return SEMDIFF_ERR_ARG; }
+  if (is_split(precision) && input_layout != SEMDIFF_INPUT_S2D_ROW4 && input_layout != SEMDIFF_INPUT_S2D_ROW2) {
+    set_error("plan_create: the split precisions need a row-window stem layout (SEMDIFF_INPUT_S2D_ROW4 / _ROW2)");
+    return SEMDIFF_ERR_UNSUPPORTED;
+  }
   if (input_layout < SEMDIFF_INPUT_NHWC8 || input_layout > SEMDIFF_INPUT_S2D16) { set_error("plan_create: bad input layout %d", input_layout); return SEMDIFF_ERR_ARG; }
   semdiff_plan* P = new semdiff_plan();
   P->input_layout = input_layout;
@@ -307,7 +318,11 @@ int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, in
   P->precision = precision;
   for (const semdiff_op& op : P->ops)
     if (op.kind == SEMDIFF_OP_TAP && op.tap + 1 > P->n_taps) P->n_taps = op.tap + 1;
-  if (P->n_taps < 1 || P->n_taps > 16) { delete P; set_error("plan_create: need 1..16 TAP ops, got %d", P->n_taps); return SEMDIFF_ERR_ARG; }
+  if (P->n_taps < 1 || P->n_taps > 16) {
+    set_error("plan_create: need 1..16 TAP ops, got %d", P->n_taps);
+    delete P;
+    return SEMDIFF_ERR_ARG;
+  }
   // tap channel counts come from a dry shape inference at a nominal size
   ShapePlan S;
   int rc = infer_shapes(P, 1, 224, 224, &S);
@@ -520,7 +535,9 @@ int semdiff_conv2d(const void* in, const void* weight, const float* bias, const 
     semdiff_plan tmp;
     tmp.precision = precision;
     impl = choose_impl(&tmp, cs);
+    if (impl < 0) { set_error("conv2d: no split-precision kernel for this shape"); return SEMDIFF_ERR_UNSUPPORTED; }
   }
+  if (is_split(precision) && impl != SEMDIFF_CONV_TC_TMA) { set_error("conv2d: split precisions run on SEMDIFF_CONV_TC_TMA only"); return SEMDIFF_ERR_UNSUPPORTED; }
   ConvPtrs q{in, in2, weight, bias, residual, out};
   switch (impl) {
     case SEMDIFF_CONV_SIMT: return launch_conv_simt(q, cs, precision, st);

@@ -37,21 +37,27 @@ class _Plan:
                  s2d_stem: bool = True, lower_kwargs: dict | None = None):
         self.lib = _lib.load()
         self.precision = _lib.PRECISIONS[precision]
-        dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[precision]
+        split = precision in _lib.SPLIT
+        dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[_lib.SPLIT.get(precision, precision)]
         self.program = trunks.LOWER[family](clip, depth, s2d_stem, **(lower_kwargs or {}))
         ops = self.program.ops
         self._keep = []
         arr = (_lib.SemdiffOp * len(ops))()
         for i, op in enumerate(ops):
             w_ptr = b_ptr = None
+            wscale = 1.0
             if op["kind"] == _lib.OP_CONV:
-                w = op["w"].to(dt).to(device).contiguous()
+                if split:
+                    w, wscale = trunks.split_weight(op["w"], dt)
+                    w = w.to(device)
+                else:
+                    w = op["w"].to(dt).to(device).contiguous()
                 b = op["b"].to(torch.float32).to(device).contiguous()
                 self._keep += [w, b]
                 w_ptr, b_ptr = w.data_ptr(), b.data_ptr()
             arr[i] = _lib.SemdiffOp(op["kind"], op["src"], op["dst"], op["res"], op["cin"], op["cout"], op["kh"],
                                     op["kw"], op["stride"], op["pad"], op["relu"], op["tap"], op["src2"], op["cin2"],
-                                    op["stride2"], op["pad_hi"], w_ptr, b_ptr)
+                                    op["stride2"], op["pad_hi"], w_ptr, b_ptr, wscale, 0)
         handle = C.c_void_p()
         _lib.check(self.lib.semdiff_plan_create(arr, len(ops), self.program.n_bufs, self.precision,
                                                 self.program.input_layout, self.program.head_ops, C.byref(handle)),
@@ -201,6 +207,10 @@ class _B200Scorer(nn.Module):
     def stem_variant(self, H: int = 224, W: int = 224):
         """Which stem lowering an image size gets: "s2d16" (compact space-to-depth input + strip kernel: 16-bit modes, even
         sizes), True (row-window layout + generic kernels: fp32 mode), False (odd sizes: channel-padded generic stem)."""
+        if self.precision in _lib.SPLIT:
+            if H % 2 or W % 2:
+                raise ValueError(f"precision={self.precision!r} needs even image sizes (got {H}x{W}); use precision='fp32' for odd sizes")
+            return True
         if H % 2 or W % 2:
             return False
         if self.precision != "fp32":
@@ -226,7 +236,7 @@ class _B200Scorer(nn.Module):
         bounds the workspace at ~8 GB (16-bit modes; the fp32 parity mode keeps 256)."""
         if self.microbatch:
             return int(self.microbatch)
-        cap = 256 if self.precision == "fp32" else 512
+        cap = 256 if self.precision == "fp32" or self.precision in _lib.SPLIT else 512
         return max(1, min(cap, (cap * 224 * 224) // max(H * W, 1)))
 
     def _run(self, a, b, head_w, head_b, want_grad: bool = False):
@@ -257,7 +267,7 @@ class _B200Scorer(nn.Module):
     def score_uint8(self, a_u8: torch.Tensor, b_u8: torch.Tensor) -> torch.Tensor:
         """forward() on decoded uint8 [N, H, W, 3] CUDA batches: `processor` runs on the device (bit-exact Pillow
         bicubic + crop + normalise), then the scorer; in the 16-bit modes the images go straight to the trunk's type."""
-        dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[self.precision]
+        dt = {"bf16": torch.bfloat16, "fp16": torch.float16}.get(self.precision, torch.float32)
         return self(self.gpu_processor(a_u8, dt), self.gpu_processor(b_u8, dt))
 
     @torch.no_grad()

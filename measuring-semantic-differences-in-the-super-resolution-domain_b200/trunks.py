@@ -11,6 +11,8 @@ otherwise a structurally identical tree with a seeded random init is built (ther
 """
 from __future__ import annotations
 
+import math
+
 import torch
 import torch.nn as nn
 
@@ -154,6 +156,22 @@ def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d, cin_pad: int | None = None
     if cin_pad is not None and cin_pad > w.shape[-1]:
         w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
     return w, beta - mean * scale
+
+
+def split_weight(w: torch.Tensor, dt16: torch.dtype):
+    """Folded fp64 weights [Cout, K] (K % 64 == 0) -> ([Cout, 2K] in `dt16`, wscale) for the split precisions
+    (include/semdiff_b200.h): w * wscale = hi + lo, stored per 64-column K block as [64 hi | 64 lo].  wscale is the power
+    of two that brings the largest weight of the layer into [1024, 2048): for fp16 that keeps the lo halves of all
+    but vanishing weights in the normal range (22 significant bits); the conv epilogue multiplies by 1/wscale."""
+    cout, k = w.shape
+    assert k % 64 == 0, "split precisions need whole 64-column K blocks"
+    wmax = float(w.abs().max())
+    scale = 2.0 ** (11 - math.frexp(wmax)[1]) if wmax > 0 else 1.0
+    ws = w * scale
+    hi = ws.to(dt16)
+    lo = (ws - hi.double()).to(dt16)
+    out = torch.stack([hi.reshape(cout, k // 64, 64), lo.reshape(cout, k // 64, 64)], dim=2)
+    return out.reshape(cout, 2 * k).contiguous(), scale
 
 
 class Program:

@@ -48,6 +48,56 @@ def test_fp32_mode_matches_oracle(trunk):
     assert e < 1e-5, (got, ref)
 
 
+def oracle_fp64(oracle, gt, sr, chunk=16):
+    """The oracle's arithmetic in fp64 (the yardstick both fp32-level implementations are measured against)."""
+    m = RestatedScorer(oracle.trunk_name, oracle.depth, seed=0)
+    m.load_state_dict(oracle.state_dict())
+    m = m.double()
+    with torch.no_grad():
+        return torch.cat([m(gt[i:i + chunk].double(), sr[i:i + chunk].double()) for i in range(0, gt.shape[0], chunk)])
+
+
+@pytest.mark.parametrize("trunk", ["resnet50", "resnet50_clip.openai"])
+def test_fp16x3_mode_matches_oracle(trunk):
+    """The split-precision tensor-core mode (three tcgen05 products per K block on hi + lo fp16 pairs) against the
+    oracle: north_star tolerance 1e-3 for the tensor-core trunk, 1e-5 for fp32-level parity."""
+    oracle, model = oracle_and_module(trunk, 3, "fp16x3")
+    gt, sr = make_pairs(8, seed=0)
+    ref = oracle(gt, sr)
+    with torch.no_grad():
+        got = model(gt.cuda(), sr.cuda()).cpu()
+    e = rel_err(got, ref)
+    r64 = oracle_fp64(oracle, gt, sr)
+    e64, o64 = rel_err(got.double(), r64), rel_err(ref.double(), r64)
+    print(f"[parity] {trunk} fp16x3 max rel err vs oracle fp32 {e:.3g}; vs fp64: ours {e64:.3g}, oracle fp32 {o64:.3g}; "
+          f"launches {model.plan().last_launches()}")
+    assert e < 1e-5, (got, ref)
+
+
+def test_fp16x3_low_sigma_and_sweep_distribution():
+    """>= 128 pairs of the sweep distribution (sigma log-uniform in [0.02, 2]) plus 32 pairs forced into the SR ~ GT corner
+    (sigma in [0.02, 0.03]) where 16-bit trunks lose the difference in their rounding: fp16x3 must hold the north_star
+    tolerance on every pair, and the rank order of the oracle."""
+    from scipy.stats import spearmanr
+    oracle, model = oracle_and_module("resnet50", 3, "fp16x3")
+    gt, sr = make_pairs(128, seed=41)
+    gt2, sr2 = make_pairs(32, seed=43, sigma_lo=0.02, sigma_hi=0.03)
+    gt, sr = torch.cat([gt, gt2]), torch.cat([sr, sr2])
+    ref = torch.cat([oracle(gt[i:i + 16], sr[i:i + 16]) for i in range(0, 160, 16)])
+    r64 = oracle_fp64(oracle, gt, sr)
+    with torch.no_grad():
+        got = model(gt.cuda(), sr.cuda()).cpu()
+    e, e_low = rel_err(got, ref), rel_err(got[128:], ref[128:])
+    e64, o64 = rel_err(got.double(), r64), rel_err(ref.double(), r64)
+    inv = lambda a, b: int((b[a.argsort()][1:] < b[a.argsort()][:-1]).sum())
+    print(f"[parity] fp16x3 over 160 pairs: max rel err vs oracle fp32 {e:.3g} (low-sigma corner {e_low:.3g}); vs fp64: ours {e64:.3g}, "
+          f"oracle fp32 {o64:.3g}; adjacent inversions vs fp64 order: ours {inv(r64, got.double())}, oracle fp32 {inv(r64, ref.double())}; "
+          f"spearman vs oracle {spearmanr(ref.numpy(), got.numpy())[0]:.9f}")
+    assert e < 1e-3 and e_low < 1e-3
+    assert e64 < 3 * o64 + 1e-5          # as close to the exact result as the reference's own fp32 path
+    assert inv(r64, got.double()) <= inv(r64, ref.double()) + 1
+
+
 def torch_16bit_error(oracle, gt, sr, ref, dtype):
     """The same oracle module run by PyTorch/cuDNN itself in `dtype` (channels_last) on this GPU: the yardstick for
     what 16-bit storage costs on these weights."""

@@ -58,7 +58,7 @@ def main():
         ops = plan.program.ops
         shapes = {0: {1: (S // 2 + 3, S // 2, 64), 2: (S // 2 + 1, S // 2, 64), 3: (S // 2, S // 2, 16)}.get(plan.program.input_layout, (S, S, 8))}
         rows, tot_conv, tot_flop = [], 0.0, 0.0
-        eb = 4 if args.precision == "fp32" else 2
+        eb = 4 if args.precision in ("fp32", "fp16x3", "bf16x3") else 2
         for i, op in enumerate(ops):
             h, w, c = shapes[op["src"]]
             t = ms[i] / args.steps
