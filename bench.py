@@ -21,6 +21,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+os.environ.setdefault("SEMDIFF_RANDOM_INIT", "1")   # synthetic benchmark: random-init weights of the named architecture
 sys.path.insert(0, ROOT)
 
 METRIC = "GT/SR pairs scored/sec (224^2, whole box)"

@@ -55,7 +55,7 @@ template <int BLOCK_N, bool kBRes = false, bool kSplit = false> struct TcCfg {
   static constexpr int GROUP_COLS = kSplit ? 64 : (BLOCK_N < 128 ? BLOCK_N : 128);   // accumulator columns per group
   static constexpr int GROUPS = BLOCK_N / GROUP_COLS;
   static constexpr int BOXES = kSplit ? 2 : GROUP_COLS / BOX_COLS;   // per group
-  static_assert(!kSplit || (BLOCK_N >= 64 && !kBRes), "split tiles: 64-column hi / lo boxes, ring-fed weights");
+  static_assert(!kSplit || (BLOCK_N >= 64 && BLOCK_N <= 128 && !kBRes), "split tiles: 64-column hi / lo boxes, ring-fed weights");
   static constexpr int BOX_BYTES = BLOCK_M * BOX_COLS * 2;
   static constexpr int GROUP_BYTES = BOXES * BOX_BYTES;
   static constexpr int RING = BLOCK_N == 256 ? 1 : (kSplit && BLOCK_N == 64 ? 2 : 3);   // non-split BLOCK_N == 256 never carries a residual
@@ -77,6 +77,7 @@ struct alignas(64) ConvTcParams {
   int num_kb1, a2_im2col, stride2;  // k-blocks [num_kb1, num_kb) come from the second source
   // split precisions: num_kb counts ring fills (3 per original k-block), num_kb1 stays in original k-blocks
   int has_src2;
+  int chunk_fills;                  // split precisions: ring fills accumulated in TMEM before the sum is promoted to registers
   float acc_scale;                  // split precisions: 1 / wscale, applied to the accumulator before the bias
 };
 static_assert(sizeof(ConvTcParams) <= 896, "ConvTcLaunch::params too small");
@@ -208,6 +209,37 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(smem_b));
     int stage = 0, phase = 0, local = 0;
     if (kBRes && blockIdx.x < total_tiles) mbar_wait(bres_bar, 0);
+    if constexpr (kSplit) {
+      // Promoted accumulation: the tensor core adds into its fp32 accumulator with truncation (measured: the error of one
+      // long accumulation grows linearly with K and is biased towards zero), so K is cut into chunks of `chunk_fills` ring
+      // fills; each chunk is accumulated from zero in one of the two TMEM stages and the epilogue warps add the chunk
+      // sums in registers (round-to-nearest) while the next chunk is being accumulated in the other stage.
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < p.num_kb;) {
+          const int acc = local & 1, acc_phase = (local >> 1) & 1;
+          ++local;
+          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+          tcgen05_fence_after();
+          const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+          const int kend = kb + p.chunk_fills < p.num_kb ? kb + p.chunk_fills : p.num_kb;
+          for (int j = 0; kb < kend; ++kb, ++j) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            if (leader) {
+              const uint64_t a_desc = a_desc0 + (uint64_t)((stage * A_STAGE_BYTES) >> 4);
+              const uint64_t b_desc = b_desc0 + (uint64_t)((stage * Cfg::B_STAGE_BYTES) >> 4);
+#pragma unroll
+              for (int k = 0; k < BLOCK_K / 16; ++k)
+                umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (j | k) != 0 ? 1u : 0u);
+              umma_commit(&empty_bar[stage]);
+              if (kb == kend - 1) umma_commit(&tmem_full_bar[acc]);
+            }
+            __syncwarp();
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -238,8 +270,33 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     int local = 0, slot = 0, sphase = 0;  // slot / sphase: position in the C ring
+    const int n_chunks = kSplit ? (p.num_kb + p.chunk_fills - 1) / p.chunk_fills : 1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      // split precisions: sums of the chunks before the last one, this warp's 32 columns of group 0 / group 1
+      float r0[kSplit ? 32 : 1], r1[kSplit ? 32 : 1];
+      if constexpr (kSplit) {
+        static_assert(!kSplit || (Cfg::GROUPS <= 2 && Cfg::GROUP_COLS / 32 == EPI_WARPS / 4), "one 32-column unit per warp and group");
+        for (int c = 0; c + 1 < n_chunks; ++c, ++local) {
+          const int cacc = local & 1;
+          mbar_wait_short(&tmem_full_bar[cacc], (local >> 1) & 1);
+          tcgen05_fence_after();
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + cacc * BLOCK_N + half * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r0[i] = c == 0 ? __uint_as_float(v[i]) : r0[i] + __uint_as_float(v[i]);
+          if constexpr (Cfg::GROUPS == 2) {
+            tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + cacc * BLOCK_N + 64 + half * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r1[i] = c == 0 ? __uint_as_float(v[i]) : r1[i] + __uint_as_float(v[i]);
+          }
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[cacc]);
+        }
+      }
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
       bool tmem_ready = false;
 #pragma unroll 1
@@ -266,6 +323,10 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
           }
           const int col0 = n_tile * BLOCK_N + col_in_tile;
           if constexpr (kSplit) {
+            if (n_chunks > 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + (g == 0 ? r0[i] : r1[i]));
+            }
             // 32 accumulator columns -> chunks j0 .. j0+3 of the group's hi box and of its lo box (same row, same chunk)
             const int j0 = col_in_group / 8;
             const uint32_t row_addr = smem_u32(cbuf) + row * 128;
@@ -618,13 +679,11 @@ template <typename T>
 static int launch_split(const ConvTcParams& p, int block_n, int a_mode, cudaStream_t st) {
   if (a_mode == A_TMA) {
     switch (block_n) {
-      case 256: return launch_t<T, 256, A_TMA, false, true>(p, st);
       case 128: return launch_t<T, 128, A_TMA, false, true>(p, st);
       case 64: return launch_t<T, 64, A_TMA, false, true>(p, st);
     }
   } else if (a_mode == A_IM2COL) {
     switch (block_n) {
-      case 256: return launch_t<T, 256, A_IM2COL, false, true>(p, st);
       case 128: return launch_t<T, 128, A_IM2COL, false, true>(p, st);
       case 64: return launch_t<T, 64, A_IM2COL, false, true>(p, st);
     }
@@ -663,13 +722,17 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   p.M = (int)s.M();
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K * (split ? 3 : 1);
-  const int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
+  int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
+  if (split && block_n > 128) block_n = 128;   // the promoted chunk sums of a 128 x 128 tile fill the epilogue warps' registers
   if (block_n == 0) { set_error("conv_tc: cout %d not a multiple of 32", s.cout); return SEMDIFF_ERR_UNSUPPORTED; }
   p.in = in; p.bias = bias; p.has_res = res != nullptr;
   p.H = s.H; p.W = s.W; p.Cin = s.cin; p.OH = s.OH(); p.OW = s.OW(); p.Cout = s.cout;
   p.KH = s.kh; p.KW = s.kw; p.stride = s.stride; p.pad = s.pad; p.relu = s.relu;
   p.n_tiles = s.cout / block_n;
   p.acc_scale = split && s.wscale > 0.f ? 1.f / s.wscale : 1.f;
+  // chunk length of the promoted accumulation in original k-blocks (3 ring fills each); SEMDIFF_X3_CHUNK_KB overrides (A/B testing)
+  static const int chunk_kb = getenv("SEMDIFF_X3_CHUNK_KB") ? atoi(getenv("SEMDIFF_X3_CHUNK_KB")) : 2;
+  p.chunk_fills = split ? 3 * (chunk_kb < 1 ? 1 : chunk_kb) : p.num_kb;
   p.cpt = s.cin / 8;
   p.taps = s.kh * s.kw;
   const uint32_t box_cols = block_n < 64 ? block_n : 64;

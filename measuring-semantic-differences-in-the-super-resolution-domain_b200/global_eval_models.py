@@ -126,8 +126,8 @@ class _B200Scorer(nn.Module):
     def _lower_kwargs(self):
         return None
 
-    def __init__(self, clip_name: str, depth: int, device: str, enc_ft: bool = False, *, precision: str = "bf16",
-                 microbatch: int | None = None, normalize: bool = False):
+    def __init__(self, clip_name: str, depth: int, device: str, enc_ft: bool = False, *, precision: str = "fp16x3",
+                 microbatch: int | None = None, normalize: bool = False, pretrained: bool | None = None):
         super().__init__()
         if enc_ft:
             raise NotImplementedError(
@@ -142,7 +142,7 @@ class _B200Scorer(nn.Module):
             raise RuntimeError(f"device={device!r}: the B200 scorer has no CPU fallback; use the reference module on CPU")
         _lib.load()  # fail loudly now if the CUDA library is missing
         self.family = trunks.trunk_family(clip_name)
-        self.clip = trunks.create_trunk(clip_name)
+        self.clip = trunks.create_trunk(clip_name, pretrained=pretrained)
         self.enc_ft = enc_ft
         self.clip.eval()
         self.clip.to(dev)

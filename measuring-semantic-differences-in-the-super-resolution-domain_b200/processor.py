@@ -10,11 +10,10 @@ import math
 def make_processor(cfg: dict):
     try:
         import timm  # noqa: PLC0415
-
-        if getattr(timm, "__version__", None):
-            return timm.data.create_transform(**timm.data.resolve_data_config(cfg), is_training=False)
-    except Exception:  # noqa: BLE001 - any failure falls through to the restated transform
-        pass
+    except ImportError:     # no timm in this environment: the restated transform below (a timm that is installed but
+        timm = None         # fails must fail loudly, not silently change the preprocessing)
+    if timm is not None and getattr(timm, "__version__", None):
+        return timm.data.create_transform(**timm.data.resolve_data_config(cfg), is_training=False)
     from torchvision import transforms as T  # noqa: PLC0415
 
     size = cfg["input_size"][-1]

@@ -12,6 +12,8 @@ otherwise a structurally identical tree with a seeded random init is built (ther
 from __future__ import annotations
 
 import math
+import os
+import warnings
 
 import torch
 import torch.nn as nn
@@ -123,16 +125,45 @@ def trunk_family(clip_name: str) -> str:
     raise ValueError(f"trunk {clip_name!r} is not supported by the B200 scorer (resnet50, resnet50_clip.openai)")
 
 
-def create_trunk(clip_name: str, seed: int = 0) -> nn.Module:
-    """timm.create_model(clip_name, pretrained=True) when a real timm is installed, else a seeded random tree."""
+def expected_keys(family: str) -> set:
+    """state_dict keys of the trunk container this package lowers (timm's names for the family)."""
+    return set(TREES[family]().state_dict().keys())
+
+
+def check_trunk_keys(clip: nn.Module, family: str):
+    """A real timm model is only usable as the parameter container if it has exactly the parameters the lowering walks
+    (the key names for resnet50_clip.openai are restated from memory of timm >= 1.0): fail at
+    construction, naming the first difference, instead of scoring with a half-lowered trunk."""
+    got = {k for k in clip.state_dict().keys() if not k.endswith("num_batches_tracked")}
+    want = {k for k in expected_keys(family) if not k.endswith("num_batches_tracked")}
+    missing, unexpected = sorted(want - got), sorted(got - want)
+    if missing or unexpected:
+        raise RuntimeError(
+            f"timm trunk {family!r} does not have the parameter names this package lowers: "
+            f"{len(missing)} missing (first: {missing[:1]}), {len(unexpected)} unexpected (first: {unexpected[:1]})")
+
+
+def create_trunk(clip_name: str, seed: int = 0, pretrained: bool | None = None) -> nn.Module:
+    """timm.create_model(clip_name, pretrained=True) - the reference's call (:315 / :689) - when a real timm is
+    installed.  Without timm there are no pretrained weights to load: that is an error unless the caller opted into a
+    seeded random-init trunk (`pretrained=False`, or SEMDIFF_RANDOM_INIT=1 as the tests and the benchmark do), because
+    scores from a random trunk are meaningless and must never appear silently."""
     family = trunk_family(clip_name)
     try:
         import timm  # noqa: PLC0415
-
-        if getattr(timm, "__version__", None):  # a real install, not a test shim
-            return timm.create_model(clip_name, pretrained=True)
     except ImportError:
-        pass
+        timm = None
+    if timm is not None and getattr(timm, "__version__", None) and pretrained is not False:  # a real install, not a test shim
+        clip = timm.create_model(clip_name, pretrained=True)
+        check_trunk_keys(clip, family)
+        return clip
+    if pretrained is None and os.environ.get("SEMDIFF_RANDOM_INIT") != "1":
+        raise RuntimeError(
+            f"timm is not installed, so the pretrained weights of {clip_name!r} cannot be loaded (the reference calls "
+            "timm.create_model(..., pretrained=True)).  Install timm, or opt into a seeded random-init trunk explicitly with "
+            "pretrained=False / SEMDIFF_RANDOM_INIT=1 and load a state_dict yourself.")
+    warnings.warn(f"semdiff_b200: {clip_name!r} trunk is a seeded RANDOM initialisation (no timm / pretrained=False); "
+                  "load a state_dict before trusting any score", stacklevel=3)
     with torch.random.fork_rng(devices=[]):
         torch.manual_seed(seed)
         tree = TREES[family]()

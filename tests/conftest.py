@@ -3,6 +3,8 @@ import sys
 
 import pytest
 
+# there is no timm (and no network) here: the trunks under test are seeded random-init trees, an explicit opt-in
+os.environ.setdefault("SEMDIFF_RANDOM_INIT", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

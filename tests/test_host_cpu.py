@@ -198,3 +198,33 @@ def test_clip_s2d16_stem_lowering_reproduces_the_3x3_stride2_conv():
     ref = bn.double().eval()(tree.stem.conv1.conv.double()(x))
     assert got.shape == ref.shape and torch.allclose(got, ref, rtol=1e-10, atol=1e-10)
     assert abs(trunks.conv_flops(prog, 224, 224) / 1e9 - 10.734452736) < 1e-9
+
+
+def test_split_weight_layout_and_resolution():
+    """Split-precision weights (include/semdiff_b200.h): per 64-column K block [64 hi | 64 lo], scaled by a power of two
+    into [1024, 2048); hi + lo reproduces the scaled fp64 weight to 2^-22 (fp16) / 2^-16 (bf16) of the layer maximum."""
+    torch.manual_seed(1)
+    w = torch.randn(96, 192, dtype=torch.float64) * 0.02
+    w[3, 5] = 1e-7    # a vanishing weight must not break anything
+    for dt, bits in ((torch.float16, 22), (torch.bfloat16, 16)):
+        s, scale = trunks.split_weight(w, dt)
+        assert s.shape == (96, 384) and s.dtype == dt
+        assert 1024 <= float((w * scale).abs().max()) < 2048 and scale == 2.0 ** round(torch.log2(torch.tensor(scale)).item())
+        v = s.double().reshape(96, 3, 2, 64)
+        assert torch.equal(v[:, :, 0, :].reshape(96, 192), (w * scale).to(dt).double())      # hi halves = the rounded weight
+        err = ((v[:, :, 0, :] + v[:, :, 1, :]).reshape(96, 192) - w * scale).abs().max() / (w * scale).abs().max()
+        assert float(err) < 2.0 ** -bits
+
+
+def test_random_init_trunk_is_an_explicit_opt_in(monkeypatch):
+    """Without timm there are no pretrained weights: constructing a trunk must raise unless the caller asked for a seeded
+    random tree (no silent random-init scores)."""
+    monkeypatch.delenv("SEMDIFF_RANDOM_INIT", raising=False)
+    with pytest.raises(RuntimeError, match="pretrained"):
+        trunks.create_trunk("resnet50")
+    with pytest.warns(UserWarning, match="RANDOM"):
+        tree = trunks.create_trunk("resnet50", pretrained=False)
+    trunks.check_trunk_keys(tree, "resnet50")
+    del tree.layer1[0].conv1
+    with pytest.raises(RuntimeError, match="1 missing"):
+        trunks.check_trunk_keys(tree, "resnet50")

@@ -65,3 +65,45 @@ def test_restated_wperlay_equals_reference_file():
     gt, sr = make_pairs(2, seed=5)
     with torch.no_grad():
         assert torch.equal(ref(gt, sr), mine(gt, sr))
+
+
+def _block2_outputs(model, x):
+    """Outputs of layer{1..4}[2] (the modules the reference hooks, :701) of a torchvision-style ResNet."""
+    outs, hooks = [], []
+    for li in range(1, 5):
+        hooks.append(getattr(model, f"layer{li}")[2].register_forward_hook(lambda m, i, o: outs.append(o)))
+    with torch.no_grad():
+        model(x)
+    for h in hooks:
+        h.remove()
+    return outs
+
+
+def test_imagenet_oracle_trunk_is_torchvision_resnet50():
+    """Pins oracle/trunks.py::resnet50 (a restatement with timm's module names): its weights loaded into
+    torchvision.models.resnet50 - and, where /root/reference exists, into the torchvision copy the reference vendors
+    (additional_approaches/src/transalnet/utils/resnet.py:326-334) - give bit-identical tap activations."""
+    import importlib.util
+
+    import torchvision
+
+    from oracle.trunks import build_trunk
+    mine = build_trunk("resnet50", seed=0, calibrate_bn=True).eval()
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(3))
+    feats = RestatedScorer("resnet50", 3, seed=0)
+    feats.clip.load_state_dict(mine.state_dict())
+    want = feats.features(x)
+    candidates = [("torchvision", torchvision.models.resnet50(weights=None))]
+    vendored = "/root/reference/additional_approaches/src/transalnet/utils/resnet.py"
+    if os.path.isfile(vendored):
+        spec = importlib.util.spec_from_file_location("_ref_vendored_resnet", vendored)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        candidates.append(("reference's vendored resnet.py", mod.resnet50(pretrained=False)))
+    for name, tv in candidates:
+        missing = tv.load_state_dict(mine.state_dict(), strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys, name
+        got = _block2_outputs(tv.eval(), x)
+        assert len(got) == 4
+        for a, b in zip(got, want):
+            assert torch.equal(a, b), name

@@ -2,6 +2,7 @@
 """PCIe / end-to-end probe: pinned H2D bandwidth and score_host() time for several chunk sizes."""
 import contextlib, io, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("SEMDIFF_RANDOM_INIT", "1")
 import torch
 import semdiff_b200
 

@@ -9,6 +9,7 @@ import os
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("SEMDIFF_RANDOM_INIT", "1")
 import torch  # noqa: E402
 
 import semdiff_b200  # noqa: E402

@@ -18,6 +18,7 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("SEMDIFF_RANDOM_INIT", "1")
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
