@@ -41,7 +41,7 @@ enum { A_TMA = 0, A_GATHER = 1, A_IM2COL = 2 };
 constexpr int MAX_RES_KB = 9;  // 9 x 64 = 576 = 3x3x64
 
 // kSplit: split precisions (hi + lo pairs of 16-bit numbers, include/semdiff_b200.h).  Every original K block is three
-// ring fills, (A hi, W hi), (A lo, W hi), (A hi, W lo), into the same accumulator; the output tile is written as 64-column
+// ring fills, (A lo, W hi), (A hi, W lo), (A hi, W hi), into the same accumulator; the output tile is written as 64-column
 // groups of two boxes, [64 hi | 64 lo] = 128 consecutive 16-bit columns of the [M, 2 Cout] output.
 template <int BLOCK_N, bool kBRes = false, bool kSplit = false> struct TcCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
@@ -178,8 +178,10 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], (kBRes ? 0 : Cfg::B_STAGE_BYTES) + (kAMode != A_GATHER ? A_STAGE_BYTES : 0));
           if (!kSplit) ko = kb;
-          const int a_lo = kSplit && term == 1;                                   // A tile: hi, lo, hi
-          const int b_blk = kSplit ? 2 * ko + (term == 2 ? 1 : 0) : kb;           // W tile: hi, hi, lo
+          // split: small products first, (A lo, W hi), (A hi, W lo), then (A hi, W hi): every tcgen05.mma output is truncated
+          // to fp32, so while the accumulator only holds the 2^-11-sized terms those truncations cost nothing
+          const int a_lo = kSplit && term == 0;
+          const int b_blk = kSplit ? 2 * ko + (term == 1 ? 1 : 0) : kb;
           if (ko >= p.num_kb1) {
             const int kb2 = kSplit ? 2 * (ko - p.num_kb1) + a_lo : ko - p.num_kb1;  // fused 1x1 conv over the second activation tensor
             if (p.a2_im2col)
@@ -731,7 +733,7 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   p.n_tiles = s.cout / block_n;
   p.acc_scale = split && s.wscale > 0.f ? 1.f / s.wscale : 1.f;
   // chunk length of the promoted accumulation in original k-blocks (3 ring fills each); SEMDIFF_X3_CHUNK_KB overrides (A/B testing)
-  static const int chunk_kb = getenv("SEMDIFF_X3_CHUNK_KB") ? atoi(getenv("SEMDIFF_X3_CHUNK_KB")) : 2;
+  static const int chunk_kb = getenv("SEMDIFF_X3_CHUNK_KB") ? atoi(getenv("SEMDIFF_X3_CHUNK_KB")) : 1;
   p.chunk_fills = split ? 3 * (chunk_kb < 1 ? 1 : chunk_kb) : p.num_kb;
   p.cpt = s.cin / 8;
   p.taps = s.kh * s.kw;

@@ -151,7 +151,7 @@ def test_layer_distance_split(shape, precision, normalize):
     got = partial[:, :parts].double().sum(1)
     rel = ((got - ref).abs() / ref).max().item()
     print(f"[split distance] {shape} {precision} normalize={normalize}: {rel:.3g}")
-    assert rel < (2e-5 if normalize else 2e-6)
+    assert rel < (5e-5 if normalize else 2e-6)   # the unit-normalisation itself runs in fp32
     if not normalize:
         refc = (split_value(act)[:n_pairs] - split_value(act)[n_pairs:]) ** 2
         assert torch.allclose(chan.double(), refc.mean(1), rtol=1e-5, atol=1e-12)
