@@ -45,3 +45,42 @@ def score_sharded(score_fn, n_pairs: int, load_pairs, group=None) -> torch.Tenso
         dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
         local = torch.empty(0, dtype=torch.float32, device=dev)
     return gather_scores(local, n_pairs, group)
+
+
+def _parse_cpulist(text: str) -> set:
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off (one process per GPU), so that the pinned host
+    buffers it allocates afterwards are first-touched on that node and every rank's H2D stream reads node-local DRAM
+    instead of all eight PCIe streams pulling from wherever the allocator happened to run.  Best effort: returns what it
+    did ({"node": n, "cpus": k}) or why not ({"skipped": reason}); never raises."""
+    import os
+
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(device_index)).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:        # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read())
+        if node < 0:
+            return {"skipped": "single NUMA node (numa_node = -1)"}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read()) & os.sched_getaffinity(0)
+        if not cpus:
+            return {"skipped": f"no allowed CPU on node {node}"}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as e:  # noqa: BLE001 - placement is an optimisation, not a requirement
+        return {"skipped": f"{type(e).__name__}: {e}"}

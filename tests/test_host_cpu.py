@@ -225,6 +225,6 @@ def test_random_init_trunk_is_an_explicit_opt_in(monkeypatch):
     with pytest.warns(UserWarning, match="RANDOM"):
         tree = trunks.create_trunk("resnet50", pretrained=False)
     trunks.check_trunk_keys(tree, "resnet50")
-    del tree.layer1[0].conv1
+    delattr(getattr(tree.layer1, "0"), "conv1")
     with pytest.raises(RuntimeError, match="1 missing"):
         trunks.check_trunk_keys(tree, "resnet50")

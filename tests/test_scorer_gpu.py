@@ -347,6 +347,92 @@ def test_high_resolution_pair_1024():
     assert torch.isfinite(s32).all() and rel_err(s16, s32) < 6e-2, (s16, s32)
 
 
+def test_high_resolution_pair_1024_vs_oracle():
+    """BASELINE.json configs[4] geometry against the CPU oracle itself (the reference is fully convolutional, :341-397): one
+    1024x1024 pair; fp32 mode and the split-precision tensor-core mode within 1e-5, the 16-bit modes bounded."""
+    oracle, m32 = oracle_and_module("resnet50", 3, "fp32")
+    g = torch.Generator().manual_seed(8)
+    gt = torch.randn(1, 3, 1024, 1024, generator=g)
+    sr = (gt + 0.05 * torch.randn(1, 3, 1024, 1024, generator=g)) / (1 + 0.0025) ** 0.5
+    ref = oracle(gt, sr)
+    got = {}
+    for precision in ("fp32", "fp16x3", "fp16", "bf16"):
+        _, m = oracle_and_module("resnet50", 3, precision)
+        with torch.no_grad():
+            got[precision] = m(gt.cuda(), sr.cuda()).cpu()
+    errs = {k: rel_err(v, ref) for k, v in got.items()}
+    print(f"[parity] 1024x1024 pair vs oracle fp32 ({ref.item():.6g}): {errs}")
+    assert errs["fp32"] < 1e-5 and errs["fp16x3"] < 1e-5 and errs["fp16"] < 2e-2 and errs["bf16"] < 0.25
+
+
+def test_goldens_fp16x3():
+    """The committed outputs of the reference itself (tests/golden/, generator oracle/make_goldens.py), split-precision mode."""
+    with open(GOLDEN) as f:
+        records = json.load(f)["records"]
+    for rec in records:
+        oracle, model = oracle_and_module(rec["trunk"], rec["depth"], "fp16x3", rec["head"])
+        gt, sr = make_pairs(rec["n_pairs"], seed=rec["input_seed"])
+        with torch.no_grad():
+            got = model(gt.cuda(), sr.cuda()).cpu()
+        ref = torch.tensor(rec["scores"])
+        scale = torch.tensor(rec["pre_relu"]).abs().clamp_min(1e-3)
+        err = ((got - ref).abs() / scale).max().item()
+        print(f"[golden] fp16x3 {rec['trunk']} depth={rec['depth']} head={rec['head']} err {err:.3g}")
+        tol = 1e-5 if rec["head"] == "abs" else 2e-3   # signed default-init heads cancel catastrophically (SURVEY 7.3)
+        assert err < tol, (rec, got)
+
+
+def test_fp16x3_invariances():
+    """Split-precision mode: a pair's score does not depend on the micro-batch, its batch position or the argument order,
+    identical images score relu(mean bias), and the head gradients match the fp32 mode's."""
+    oracle, model = oracle_and_module("resnet50", 2, "fp16x3")
+    gt, sr = make_pairs(6, seed=9)
+    gt, sr = gt.cuda(), sr.cuda()
+    with torch.no_grad():
+        model.microbatch = 6
+        full = model(gt, sr)
+        model.microbatch = 4          # ragged: 4 + 2
+        ragged = model(gt, sr)
+        single = torch.cat([model(gt[i:i + 1], sr[i:i + 1]) for i in range(6)])
+        swapped = model(sr, gt)
+        same = model(gt, gt)
+    assert torch.equal(full, ragged) and torch.equal(full, single) and torch.equal(full, swapped)
+    bias = torch.stack([m.bias.detach().reshape(()) for m in model.w_layers]).mean()
+    assert torch.allclose(same, torch.relu(bias).expand(6), rtol=0, atol=1e-7)
+    _, m32 = oracle_and_module("resnet50", 2, "fp32")
+    target = torch.linspace(0.0, 1.0, 6).cuda()
+    for m in (model, m32):
+        m.zero_grad()
+        torch.nn.functional.mse_loss(m(gt, sr), target).backward()
+    for a, b in zip(model.w_layers, m32.w_layers):
+        assert torch.allclose(a.weight.grad, b.weight.grad, rtol=1e-4, atol=1e-9)
+        assert torch.allclose(a.bias.grad, b.bias.grad, rtol=1e-4, atol=1e-9)
+    with pytest.raises(ValueError, match="even image sizes"):
+        model(gt[:, :, :223], sr[:, :, :223])
+
+
+def test_normalize_has_no_gradient_path():
+    """the LPIPS-style normalised variant must not hand back gradients of the un-normalised function."""
+    model = CLS["resnet50"]("resnet50", 0, "cuda", precision="bf16", normalize=True)
+    gt, sr = make_pairs(2, seed=3)
+    with pytest.raises(NotImplementedError, match="normalize"):
+        model(gt.cuda(), sr.cuda())
+    with torch.no_grad():
+        assert torch.isfinite(model(gt.cuda(), sr.cuda())).all()
+
+
+def test_score_host_uint8_matches_device_path():
+    """score_host on decoded uint8 host images == gpu_processor + forward on the device (same kernels, chunked + staged)."""
+    oracle, model = oracle_and_module("resnet50", 3, "bf16")
+    g = torch.Generator().manual_seed(5)
+    a = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()
+    b = torch.randint(0, 256, (5, 224, 224, 3), dtype=torch.uint8, generator=g).pin_memory()
+    with torch.no_grad():
+        want = model.score_uint8(a.cuda(), b.cuda()).cpu()
+        got = model.score_host(a, b, chunk_pairs=2)
+    assert torch.equal(got, want)
+
+
 def test_c_abi_error_paths():
     """Every failure is a negative return code + message, never a crash or a silent fallback."""
     import ctypes as C

@@ -35,6 +35,11 @@ with open(out_md, "w") as f:
     f.write(f"distance_kernel: {len(dist)} launches, {sum(g(d,'gpu__time_duration.sum') for d in dist):.0f} us, DRAM "
             f"{sum(g(d,'dram__bytes_read.sum')+g(d,'dram__bytes_write.sum') for d in dist)/1e9:.2f} GB (algorithmic 1.54 GB).\n")
 if len(sys.argv) > 4:
-    json.dump({"conv_tc_dram_bytes_per_launch": cb / len(conv), "conv_tc_launches": len(conv), "conv_tc_dram_bytes_per_step": cb,
+    # the digest of the kernel sources that were profiled (written on the GPU box by tools/gpu_ncu_light.sh next to the CSV):
+    # bench.py quotes the traffic figure only while csrc/ still hashes to it
+    import os
+    dig = os.path.splitext(src)[0] + ".digest"
+    stamp = open(dig).read().strip() if os.path.isfile(dig) else None
+    json.dump({"kernel_sources_sha256": stamp, "conv_tc_dram_bytes_per_launch": cb / len(conv), "conv_tc_launches": len(conv), "conv_tc_dram_bytes_per_step": cb,
                "conv_tc_share_of_step_under_ncu": ct / tot, "time_weighted_tensor_pipe_pct": tw, "source": out_md}, open(sys.argv[4], "w"), indent=1)
 print(open(out_md).read()[-600:])
