@@ -14,8 +14,8 @@ REPO = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libsemdiff_b200.so")
 STAMP = LIB_PATH + ".stamp"
-SOURCES = ["plan.cu", "conv_tc.cu", "conv_simt.cu", "distance.cu", "elementwise.cu", "preprocess.cu", "conv3x3_strip.cu", "conv_chain.cu"]
-HEADERS = ["common.cuh", "kernels.h", os.path.join(REPO, "include", "semdiff_b200.h")]
+SOURCES = ["plan.cu", "conv_tc.cu", "conv_simt.cu", "distance.cu", "elementwise.cu", "preprocess.cu", "conv3x3_strip.cu", "conv_chain.cu", "conv_tc_split.cu"]
+HEADERS = ["common.cuh", "kernels.h", "conv_tc.h", os.path.join(REPO, "include", "semdiff_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-I", os.path.join(REPO, "include"), "-I", CSRC]
 

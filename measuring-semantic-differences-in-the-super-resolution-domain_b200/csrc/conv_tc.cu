@@ -25,25 +25,16 @@
 #include <cuda.h>
 #include <stdlib.h>
 
-#include "common.cuh"
-#include "kernels.h"
+#include "conv_tc.h"
 
 namespace semdiff {
-
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;  // 64 x 16-bit = one 128-byte swizzle row
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-enum { A_TMA = 0, A_GATHER = 1, A_IM2COL = 2 };
 
 // kBRes ("B resident"): the whole weight matrix of the conv (one n-tile, <= MAX_RES_KB k-blocks) is loaded into shared
 // memory ONCE per CTA and the ring only cycles activation tiles - for the 64-output-channel convs (stems, layer1 3x3s)
 // whose tiles are bound by L2->SM operand traffic, this removes a third of it and doubles the ring depth.
 constexpr int MAX_RES_KB = 9;  // 9 x 64 = 576 = 3x3x64
 
-// kSplit: split precisions (hi + lo pairs of 16-bit numbers, include/semdiff_b200.h).  Every original K block is three
-// ring fills, (A lo, W hi), (A hi, W lo), (A hi, W hi), into the same accumulator; the output tile is written as 64-column
-// groups of two boxes, [64 hi | 64 lo] = 128 consecutive 16-bit columns of the [M, 2 Cout] output.
-template <int BLOCK_N, bool kBRes = false, bool kSplit = false> struct TcCfg {
+template <int BLOCK_N, bool kBRes = false> struct TcCfg {
   static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + (kBRes ? 0 : B_STAGE_BYTES);
   static constexpr int STAGES = kBRes ? 6 : (BLOCK_N >= 128 ? 4 : 6);
@@ -52,41 +43,16 @@ template <int BLOCK_N, bool kBRes = false, bool kSplit = false> struct TcCfg {
   static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   // epilogue staging: the tile is written out in column groups, each group = BOXES TMA boxes of BOX_COLS columns
   static constexpr int BOX_COLS = BLOCK_N < 64 ? BLOCK_N : 64;
-  static constexpr int GROUP_COLS = kSplit ? 64 : (BLOCK_N < 128 ? BLOCK_N : 128);   // accumulator columns per group
+  static constexpr int GROUP_COLS = BLOCK_N < 128 ? BLOCK_N : 128;
   static constexpr int GROUPS = BLOCK_N / GROUP_COLS;
-  static constexpr int BOXES = kSplit ? 2 : GROUP_COLS / BOX_COLS;   // per group
-  static_assert(!kSplit || (BLOCK_N >= 64 && BLOCK_N <= 128 && !kBRes), "split tiles: 64-column hi / lo boxes, ring-fed weights");
+  static constexpr int BOXES = GROUP_COLS / BOX_COLS;   // per group
   static constexpr int BOX_BYTES = BLOCK_M * BOX_COLS * 2;
   static constexpr int GROUP_BYTES = BOXES * BOX_BYTES;
-  static constexpr int RING = BLOCK_N == 256 ? 1 : (kSplit && BLOCK_N == 64 ? 2 : 3);   // non-split BLOCK_N == 256 never carries a residual
+  static constexpr int RING = BLOCK_N == 256 ? 1 : 3;   // BLOCK_N == 256 never carries a residual
   static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RING + 1;
   static constexpr int SMEM_BYTES = STAGES * A_STAGE_BYTES + B_REGION_BYTES + RING * GROUP_BYTES + NUM_BARS * 8 + 16 + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
-
-struct alignas(64) ConvTcParams {
-  CUtensorMap tmA;  // activations: [M, Cin] tiled (A_TMA) or NHWC im2col (A_IM2COL)
-  CUtensorMap tmA2; // fused second source (1x1 conv): [M, Cin2] tiled when stride2 == 1, else NHWC im2col
-  CUtensorMap tmB;  // weights as [Cout, K]
-  CUtensorMap tmC;  // output as [M, Cout]
-  CUtensorMap tmR;  // residual as [M, Cout]
-  const void* in;
-  const float* bias;
-  int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, relu, has_res;
-  int M, num_kb, m_tiles, n_tiles, cpt, taps;
-  int num_kb1, a2_im2col, stride2;  // k-blocks [num_kb1, num_kb) come from the second source
-  // split precisions: num_kb counts ring fills (3 per original k-block), num_kb1 stays in original k-blocks
-  int has_src2;
-  int chunk_fills;                  // split precisions: ring fills accumulated in TMEM before the sum is promoted to registers
-  float acc_scale;                  // split precisions: 1 / wscale, applied to the accumulator before the bias
-};
-static_assert(sizeof(ConvTcParams) <= 896, "ConvTcLaunch::params too small");
-
-// 16-byte chunk position inside a swizzled row of ROW_BYTES (128 B -> SWIZZLE_128B, 64 B -> SWIZZLE_64B)
-template <int ROW_BYTES> __device__ __forceinline__ uint32_t swz_chunk(uint32_t chunk, uint32_t row) {
-  if constexpr (ROW_BYTES == 128) return chunk ^ (row & 7);
-  else return chunk ^ ((row >> 1) & 3);
-}
 
 // epilogue warps: 8 (two per TMEM lane quarter, splitting the columns) except where warps 6-9 are the gather producers
 template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int epi_warps() { return (kAMode == A_GATHER || BLOCK_N < 64) ? 4 : 8; }
@@ -94,10 +60,9 @@ template <int BLOCK_N, int kAMode> __host__ __device__ constexpr int cta_threads
   return kAMode == A_GATHER ? 352 : (2 + epi_warps<BLOCK_N, kAMode>() + 1) * 32;
 }
 
-template <typename T, int BLOCK_N, int kAMode, bool kBRes = false, bool kSplit = false>
+template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
 __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_kernel(const __grid_constant__ ConvTcParams p) {
-  using Cfg = TcCfg<BLOCK_N, kBRes, kSplit>;
-  static_assert(!kSplit || kAMode != A_GATHER, "split precisions take their activations through TMA");
+  using Cfg = TcCfg<BLOCK_N, kBRes>;
   constexpr int EPI_WARPS = epi_warps<BLOCK_N, kAMode>();
   constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING;
   extern __shared__ uint8_t smem_raw[];
@@ -173,32 +138,25 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
           w2 = ow * p.stride2;
         }
         int tap = 0, cb = 0;  // filter tap and 64-channel block of the current k-block (im2col)
-        int ko = 0, term = 0;  // split: original k-block and which of its three products this fill feeds
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_arrive_expect_tx(&full_bar[stage], (kBRes ? 0 : Cfg::B_STAGE_BYTES) + (kAMode != A_GATHER ? A_STAGE_BYTES : 0));
-          if (!kSplit) ko = kb;
-          // split: small products first, (A lo, W hi), (A hi, W lo), then (A hi, W hi): every tcgen05.mma output is truncated
-          // to fp32, so while the accumulator only holds the 2^-11-sized terms those truncations cost nothing
-          const int a_lo = kSplit && term == 0;
-          const int b_blk = kSplit ? 2 * ko + (term == 1 ? 1 : 0) : kb;
-          if (ko >= p.num_kb1) {
-            const int kb2 = kSplit ? 2 * (ko - p.num_kb1) + a_lo : ko - p.num_kb1;  // fused 1x1 conv over the second activation tensor
+          if (kb >= p.num_kb1) {
+            const int kb2 = kb - p.num_kb1;  // fused 1x1 conv over the second activation tensor
             if (p.a2_im2col)
               tma_load_im2col_4d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb2 * BLOCK_K, w2, h2, n, 0, 0);
             else
               tma_load_2d(&p.tmA2, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb2 * BLOCK_K, m_tile * BLOCK_M);
           } else if (kAMode == A_TMA) {
-            tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, (kSplit ? 2 * ko + a_lo : ko) * BLOCK_K, m_tile * BLOCK_M);
+            tma_load_2d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kb * BLOCK_K, m_tile * BLOCK_M);
           } else if (kAMode == A_IM2COL) {
             const int r = tap / p.KW, s = tap - r * p.KW;
-            tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, (kSplit ? 2 * cb + a_lo : cb) * BLOCK_K, w0, h0, n,
+            tma_load_im2col_4d(&p.tmA, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, cb * BLOCK_K, w0, h0, n,
                                (uint16_t)s, (uint16_t)r);
-            if (!kSplit || term == 2) { if (++cb == kb_per_tap) { cb = 0; ++tap; } }
+            if (++cb == kb_per_tap) { cb = 0; ++tap; }
           }
           if (!kBRes)
-            tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, b_blk * BLOCK_K, n_tile * BLOCK_N);
-          if (kSplit && ++term == 3) { term = 0; ++ko; }
+            tma_load_2d(&p.tmB, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, kb * BLOCK_K, n_tile * BLOCK_N);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -211,37 +169,6 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const uint64_t b_desc0 = umma_smem_desc_sw128(smem_u32(smem_b));
     int stage = 0, phase = 0, local = 0;
     if (kBRes && blockIdx.x < total_tiles) mbar_wait(bres_bar, 0);
-    if constexpr (kSplit) {
-      // Promoted accumulation: the tensor core adds into its fp32 accumulator with truncation (measured: the error of one
-      // long accumulation grows linearly with K and is biased towards zero), so K is cut into chunks of `chunk_fills` ring
-      // fills; each chunk is accumulated from zero in one of the two TMEM stages and the epilogue warps add the chunk
-      // sums in registers (round-to-nearest) while the next chunk is being accumulated in the other stage.
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < p.num_kb;) {
-          const int acc = local & 1, acc_phase = (local >> 1) & 1;
-          ++local;
-          mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
-          tcgen05_fence_after();
-          const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-          const int kend = kb + p.chunk_fills < p.num_kb ? kb + p.chunk_fills : p.num_kb;
-          for (int j = 0; kb < kend; ++kb, ++j) {
-            mbar_wait(&full_bar[stage], phase);
-            tcgen05_fence_after();
-            if (leader) {
-              const uint64_t a_desc = a_desc0 + (uint64_t)((stage * A_STAGE_BYTES) >> 4);
-              const uint64_t b_desc = b_desc0 + (uint64_t)((stage * Cfg::B_STAGE_BYTES) >> 4);
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / 16; ++k)
-                umma_f16_ss(tmem_d, a_desc + (uint64_t)(k * 2), b_desc + (uint64_t)(k * 2), idesc, (j | k) != 0 ? 1u : 0u);
-              umma_commit(&empty_bar[stage]);
-              if (kb == kend - 1) umma_commit(&tmem_full_bar[acc]);
-            }
-            __syncwarp();
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    } else
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
@@ -272,33 +199,8 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
     const int half = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     int local = 0, slot = 0, sphase = 0;  // slot / sphase: position in the C ring
-    const int n_chunks = kSplit ? (p.num_kb + p.chunk_fills - 1) / p.chunk_fills : 1;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++local) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      // split precisions: sums of the chunks before the last one, this warp's 32 columns of group 0 / group 1
-      float r0[kSplit ? 32 : 1], r1[kSplit ? 32 : 1];
-      if constexpr (kSplit) {
-        static_assert(!kSplit || (Cfg::GROUPS <= 2 && Cfg::GROUP_COLS / 32 == EPI_WARPS / 4), "one 32-column unit per warp and group");
-        for (int c = 0; c + 1 < n_chunks; ++c, ++local) {
-          const int cacc = local & 1;
-          mbar_wait_short(&tmem_full_bar[cacc], (local >> 1) & 1);
-          tcgen05_fence_after();
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + cacc * BLOCK_N + half * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) r0[i] = c == 0 ? __uint_as_float(v[i]) : r0[i] + __uint_as_float(v[i]);
-          if constexpr (Cfg::GROUPS == 2) {
-            tmem_ld_32x32b_x32(tmem_base + (uint32_t(q * 32) << 16) + cacc * BLOCK_N + 64 + half * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r1[i] = c == 0 ? __uint_as_float(v[i]) : r1[i] + __uint_as_float(v[i]);
-          }
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[cacc]);
-        }
-      }
       const int acc = local & 1, acc_phase = (local >> 1) & 1;
       bool tmem_ready = false;
 #pragma unroll 1
@@ -324,48 +226,6 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
           }
           const int col0 = n_tile * BLOCK_N + col_in_tile;
-          if constexpr (kSplit) {
-            if (n_chunks > 1) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + (g == 0 ? r0[i] : r1[i]));
-            }
-            // 32 accumulator columns -> chunks j0 .. j0+3 of the group's hi box and of its lo box (same row, same chunk)
-            const int j0 = col_in_group / 8;
-            const uint32_t row_addr = smem_u32(cbuf) + row * 128;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
-              const float sc = p.acc_scale;   // a power of two: exact
-              float f[8] = {fmaf(__uint_as_float(v[j * 8 + 0]), sc, b0.x), fmaf(__uint_as_float(v[j * 8 + 1]), sc, b0.y),
-                            fmaf(__uint_as_float(v[j * 8 + 2]), sc, b0.z), fmaf(__uint_as_float(v[j * 8 + 3]), sc, b0.w),
-                            fmaf(__uint_as_float(v[j * 8 + 4]), sc, b1.x), fmaf(__uint_as_float(v[j * 8 + 5]), sc, b1.y),
-                            fmaf(__uint_as_float(v[j * 8 + 6]), sc, b1.z), fmaf(__uint_as_float(v[j * 8 + 7]), sc, b1.w)};
-              const uint32_t a_hi = row_addr + (swz_chunk<128>(j0 + j, row) << 4), a_lo = a_hi + Cfg::BOX_BYTES;
-              if (p.has_res) {
-                uint4 rh, rl;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rh.x), "=r"(rh.y), "=r"(rh.z), "=r"(rh.w) : "r"(a_hi));
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(rl.x), "=r"(rl.y), "=r"(rl.z), "=r"(rl.w) : "r"(a_lo));
-                float h[8], l[8];
-                unpack8<T>(rh, h);
-                unpack8<T>(rl, l);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] += h[e] + l[e];
-              }
-              if (p.relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-              }
-              const uint4 oh = pack8<T>(f);
-              float h[8];
-              unpack8<T>(oh, h);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) h[e] = f[e] - h[e];   // exact: hi is f rounded to fewer bits
-              const uint4 ol = pack8<T>(h);
-              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_hi), "r"(oh.x), "r"(oh.y), "r"(oh.z), "r"(oh.w) : "memory");
-              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(a_lo), "r"(ol.x), "r"(ol.y), "r"(ol.z), "r"(ol.w) : "memory");
-            }
-          } else {
           const int box = col_in_group / Cfg::BOX_COLS, j0 = (col_in_group % Cfg::BOX_COLS) / 8;
           const uint32_t row_addr = smem_u32(cbuf + box * Cfg::BOX_BYTES) + row * ROW_BYTES;
 #pragma unroll
@@ -391,7 +251,6 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
             }
             const uint4 o = pack8<T>(f);
             asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-          }
           }
         }
         // this warp's part of the slot is staged: make it visible to the async proxy (TMA store), then publish
@@ -419,8 +278,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
 #pragma unroll
             for (int b = 0; b < Cfg::BOXES; ++b)
               tma_load_2d(&p.tmR, &res_full_bar[l_slot], cbuf + b * Cfg::BOX_BYTES,
-                          kSplit ? 2 * (n_tile * BLOCK_N + l_g * Cfg::GROUP_COLS) + b * 64 : n_tile * BLOCK_N + l_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
-                          m_tile * BLOCK_M);
+                          n_tile * BLOCK_N + l_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS, m_tile * BLOCK_M);
           } else {
             mbar_arrive(&res_full_bar[l_slot]);
           }
@@ -434,8 +292,7 @@ __global__ void __launch_bounds__(cta_threads<BLOCK_N, kAMode>(), 1) conv_tc_ker
           uint8_t* cbuf = smem_c + s_slot * Cfg::GROUP_BYTES;
 #pragma unroll
           for (int b = 0; b < Cfg::BOXES; ++b)
-            tma_store_2d(&p.tmC, cbuf + b * Cfg::BOX_BYTES,
-                         kSplit ? 2 * (n_tile * BLOCK_N + s_g * Cfg::GROUP_COLS) + b * 64 : n_tile * BLOCK_N + s_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
+            tma_store_2d(&p.tmC, cbuf + b * Cfg::BOX_BYTES, n_tile * BLOCK_N + s_g * Cfg::GROUP_COLS + b * Cfg::BOX_COLS,
                          m_tile * BLOCK_M);
         }
         bulk_commit();
@@ -628,14 +485,12 @@ bool conv_tc_supported(const ConvShape& s, int precision, bool use_tma) {
   return s.M() > 0 && s.M() < (int64_t)1 << 31;
 }
 
-// per-device caches (a process may drive several GPUs; function attributes and SM counts are per device)
-constexpr int MAX_DEVICES = 64;
-static int current_device() {
+int current_device() {
   int dev = 0;
   cudaGetDevice(&dev);
   return dev >= 0 && dev < MAX_DEVICES ? dev : 0;
 }
-static int num_sms() {
+int num_sms() {
   static int sms[MAX_DEVICES] = {};
   const int dev = current_device();
   if (sms[dev] == 0) {
@@ -645,11 +500,11 @@ static int num_sms() {
   return sms[dev];
 }
 
-template <typename T, int BLOCK_N, int kAMode, bool kBRes = false, bool kSplit = false>
+template <typename T, int BLOCK_N, int kAMode, bool kBRes = false>
 static int launch_t(const ConvTcParams& p, cudaStream_t st) {
-  using Cfg = TcCfg<BLOCK_N, kBRes, kSplit>;
+  using Cfg = TcCfg<BLOCK_N, kBRes>;
   static bool configured[MAX_DEVICES] = {};
-  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode, kBRes, kSplit>;
+  auto kern = conv_tc_kernel<T, BLOCK_N, kAMode, kBRes>;
   const int dev = current_device();
   if (!configured[dev]) {
     SEMDIFF_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -674,23 +529,6 @@ static int launch_n(const ConvTcParams& p, int block_n, cudaStream_t st) {
     case 32: return launch_t<T, 32, kAMode>(p, st);
   }
   set_error("conv_tc: unsupported BLOCK_N %d", block_n);
-  return SEMDIFF_ERR_UNSUPPORTED;
-}
-
-template <typename T>
-static int launch_split(const ConvTcParams& p, int block_n, int a_mode, cudaStream_t st) {
-  if (a_mode == A_TMA) {
-    switch (block_n) {
-      case 128: return launch_t<T, 128, A_TMA, false, true>(p, st);
-      case 64: return launch_t<T, 64, A_TMA, false, true>(p, st);
-    }
-  } else if (a_mode == A_IM2COL) {
-    switch (block_n) {
-      case 128: return launch_t<T, 128, A_IM2COL, false, true>(p, st);
-      case 64: return launch_t<T, 64, A_IM2COL, false, true>(p, st);
-    }
-  }
-  set_error("conv_tc (split): unsupported tile %d / mode %d", block_n, a_mode);
   return SEMDIFF_ERR_UNSUPPORTED;
 }
 
@@ -723,25 +561,25 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   const int kmul = split ? 2 : 1;    // stored 16-bit columns per logical channel
   p.M = (int)s.M();
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
-  p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K * (split ? 3 : 1);
-  int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
-  if (split && block_n > 128) block_n = 128;   // the promoted chunk sums of a 128 x 128 tile fill the epilogue warps' registers
+  p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K;
+  // split: a k-block is 12 MMAs instead of 4, so the 256-wide tile pays off from K = 128 on
+  const int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb * (split ? 3 : 1), p.m_tiles, num_sms());
   if (block_n == 0) { set_error("conv_tc: cout %d not a multiple of 32", s.cout); return SEMDIFF_ERR_UNSUPPORTED; }
   p.in = in; p.bias = bias; p.has_res = res != nullptr;
   p.H = s.H; p.W = s.W; p.Cin = s.cin; p.OH = s.OH(); p.OW = s.OW(); p.Cout = s.cout;
   p.KH = s.kh; p.KW = s.kw; p.stride = s.stride; p.pad = s.pad; p.relu = s.relu;
   p.n_tiles = s.cout / block_n;
   p.acc_scale = split && s.wscale > 0.f ? 1.f / s.wscale : 1.f;
-  // chunk length of the promoted accumulation in original k-blocks (3 ring fills each); SEMDIFF_X3_CHUNK_KB overrides (A/B testing)
+  // chunk length of the promoted accumulation in k-blocks; SEMDIFF_X3_CHUNK_KB overrides (A/B testing)
   static const int chunk_kb = getenv("SEMDIFF_X3_CHUNK_KB") ? atoi(getenv("SEMDIFF_X3_CHUNK_KB")) : 1;
-  p.chunk_fills = split ? 3 * (chunk_kb < 1 ? 1 : chunk_kb) : p.num_kb;
+  p.chunk_kb = chunk_kb < 1 ? 1 : chunk_kb;
   p.cpt = s.cin / 8;
   p.taps = s.kh * s.kw;
   const uint32_t box_cols = block_n < 64 ? block_n : 64;
   int rc = make_tmap_2d(&p.tmB, w, precision, (uint64_t)s.cout, (uint64_t)s.K() * kmul, BLOCK_K, (uint32_t)block_n);
   if (rc == 0 && a_mode == A_TMA) rc = make_tmap_2d(&p.tmA, in, precision, (uint64_t)p.M, (uint64_t)s.cin * kmul, BLOCK_K, BLOCK_M);
   if (rc == 0 && a_mode == A_IM2COL) rc = make_tmap_im2col(&p.tmA, in, precision, s, false);
-  p.num_kb1 = (s.K() + BLOCK_K - 1) / BLOCK_K;   // original k-blocks (the producer counts in these)
+  p.num_kb1 = p.num_kb;
   p.stride2 = 1;
   if (rc == 0 && s.cin2 != 0) {
     p.num_kb1 = s.K1() / BLOCK_K;
@@ -767,8 +605,8 @@ int conv_tc_launch(const ConvTcLaunch* L, cudaStream_t st) {
   switch (L->precision) {
     case SEMDIFF_BF16: return launch_mode<__nv_bfloat16>(p, L->block_n, L->a_mode, st);
     case SEMDIFF_FP16: return launch_mode<__half>(p, L->block_n, L->a_mode, st);
-    case SEMDIFF_FP16X3: return launch_split<__half>(p, L->block_n, L->a_mode, st);
-    case SEMDIFF_BF16X3: return launch_split<__nv_bfloat16>(p, L->block_n, L->a_mode, st);
+    case SEMDIFF_FP16X3:
+    case SEMDIFF_BF16X3: return launch_conv_split(p, L->block_n, L->a_mode, L->precision, st);
   }
   set_error("conv_tc: bad precision %d", L->precision);
   return SEMDIFF_ERR_ARG;
