@@ -288,27 +288,35 @@ __global__ void __launch_bounds__(256) maxpool_split_kernel(const T* __restrict_
     const int p = i / cv;
     const int oh = p / OW, ow = p - oh * OW;
     const int so = split_off(c8);
-    float mh[8], ml[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) { mh[k] = -INFINITY; ml[k] = 0.f; }
+    // all 18 loads are unconditional and in flight together: a tap outside the image is replaced by the window centre,
+    // which is always valid (max is idempotent)
+    uint4 qh[9], ql[9];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const int ih = oh * 2 - 1 + r;
-      if (ih < 0 || ih >= H) continue;
+      int ih = oh * 2 - 1 + r;
+      ih = (ih < 0 || ih >= H) ? oh * 2 : ih;
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        const int iw = ow * 2 - 1 + s;
-        if (iw < 0 || iw >= W) continue;
+        int iw = ow * 2 - 1 + s;
+        iw = (iw < 0 || iw >= W) ? ow * 2 : iw;
         const T* px = img_in + ((int64_t)ih * W + iw) * C * 2 + so;
-        float h[8], l[8];
-        unpack8<T>(*reinterpret_cast<const uint4*>(px), h);
-        unpack8<T>(*reinterpret_cast<const uint4*>(px + 64), l);
+        qh[r * 3 + s] = __ldg(reinterpret_cast<const uint4*>(px));        // neighbouring outputs share taps: keep them in L1
+        ql[r * 3 + s] = __ldg(reinterpret_cast<const uint4*>(px + 64));
+      }
+    }
+    float mh[8], ml[8];
+    unpack8<T>(qh[0], mh);
+    unpack8<T>(ql[0], ml);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const bool better = h[k] > mh[k] || (h[k] == mh[k] && l[k] > ml[k]);
-          mh[k] = better ? h[k] : mh[k];
-          ml[k] = better ? l[k] : ml[k];
-        }
+    for (int t = 1; t < 9; ++t) {
+      float h[8], l[8];
+      unpack8<T>(qh[t], h);
+      unpack8<T>(ql[t], l);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const bool better = h[k] > mh[k] || (h[k] == mh[k] && l[k] > ml[k]);
+        mh[k] = better ? h[k] : mh[k];
+        ml[k] = better ? l[k] : ml[k];
       }
     }
     T* dst = img_out + (int64_t)p * C * 2 + so;
