@@ -58,7 +58,15 @@ enum {
 /* One step of the trunk program.  Buffers are logical ids in [0, n_bufs); buffer 0 is the packed
  * input image batch.  The program is what /root/reference/models/global_eval_models.py:364,371
  * (self.clip(a), self.clip(b)) executes inside timm, with BatchNorm folded. */
-enum { SEMDIFF_OP_CONV = 0, SEMDIFF_OP_MAXPOOL3S2 = 1, SEMDIFF_OP_AVGPOOL = 2, SEMDIFF_OP_TAP = 3 };
+enum {
+  SEMDIFF_OP_CONV = 0, SEMDIFF_OP_MAXPOOL3S2 = 1, SEMDIFF_OP_AVGPOOL = 2, SEMDIFF_OP_TAP = 3,
+  /* local-map decoder (/root/reference/models/local_eval_models.py:109-125): buffers written by SQDIFF hold ONE image per
+   * pair (everything downstream of it too); all other buffers hold two (GT image, SR image) */
+  SEMDIFF_OP_SQDIFF = 4,     /* dst[pair] = (src[GT image] - src[SR image])^2                      (:115) */
+  SEMDIFF_OP_CONCAT = 5,     /* dst = channel concat (src | src2); cin / cin2 = their channel counts (:121) */
+  SEMDIFF_OP_UPSAMPLE2X = 6, /* nn.UpsamplingBilinear2d(scale_factor=2): bilinear, align_corners   (:84, :119, :123) */
+  SEMDIFF_OP_MAP_OUT = 7     /* channel 0 of src -> bilinear x2 -> sigmoid -> the fp32 output map   (:123-125) */
+};
 
 typedef struct semdiff_op {
   int32_t kind;      /* SEMDIFF_OP_* */
@@ -114,6 +122,13 @@ int semdiff_score(semdiff_plan* plan, const void* gt, const void* sr, int32_t in
                   void* workspace, int64_t workspace_bytes, float* out_scores, float* out_pre_relu,
                   float* out_chan_mean, semdiff_stream_t stream);
 
+/* Local maps (CLIP_lpips_Unet, /root/reference/models/local_eval_models.py:86-126): runs a program that ends in
+ * SEMDIFF_OP_MAP_OUT.  out_map: device fp32 [n_pairs, 1, Hm, Wm], Hm x Wm = twice the size of MAP_OUT's source (= H x W for
+ * the reference's decoders).  Other arguments as semdiff_score. */
+int semdiff_score_map(semdiff_plan* plan, const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H,
+                      int32_t W, int32_t microbatch_pairs, void* workspace, int64_t workspace_bytes, float* out_map,
+                      semdiff_stream_t stream);
+
 /* Profiling: when enabled, semdiff_score brackets every op with CUDA events on `stream`. */
 int semdiff_plan_set_profiling(semdiff_plan* plan, int32_t enable);
 /* Per-op accumulated milliseconds and launch counts since the last reset (arrays of n_ops + 3:
@@ -167,6 +182,11 @@ int semdiff_maxpool3x3s2(const void* in, void* out, int32_t n_img, int32_t H, in
                          int32_t precision, semdiff_stream_t stream);
 int semdiff_avgpool(const void* in, void* out, int32_t n_img, int32_t H, int32_t W, int32_t c, int32_t window,
                     int32_t precision, semdiff_stream_t stream);
+
+/* One decoder helper (unit tests; the plan calls the same launcher): what = 0 SQDIFF (n_img = pairs; in holds 2 * n_img
+ * images), 1 CONCAT (c | c2), 2 UPSAMPLE2X, 3 MAP_OUT (out = fp32 [n_img, 1, 2H, 2W]).  NHWC, element type per precision. */
+int semdiff_decoder_op(int32_t what, const void* in, const void* in2, void* out, int32_t n_img, int32_t H, int32_t W,
+                       int32_t c, int32_t c2, int32_t precision, semdiff_stream_t stream);
 
 /* Fused per-layer distance (:379-384 / :755-760): act = NHWC [2*n_pairs, HW, C] with GT image i at
  * index i and SR image i at index n_pairs + i.  Writes partial[pair * SEMDIFF_MAX_PARTS + part] =

@@ -13,7 +13,7 @@ BF16, FP16, FP32, FP16X3, BF16X3 = 0, 1, 2, 3, 4
 PRECISIONS = {"bf16": BF16, "fp16": FP16, "fp32": FP32, "fp16x3": FP16X3, "bf16x3": BF16X3}
 SPLIT = {"fp16x3": "fp16", "bf16x3": "bf16"}   # split precisions -> the 16-bit type of their hi / lo halves
 CONV_AUTO, CONV_SIMT, CONV_TC_GATHER, CONV_TC_TMA = 0, 1, 2, 3
-OP_CONV, OP_MAXPOOL3S2, OP_AVGPOOL, OP_TAP = 0, 1, 2, 3
+OP_CONV, OP_MAXPOOL3S2, OP_AVGPOOL, OP_TAP, OP_SQDIFF, OP_CONCAT, OP_UPSAMPLE2X, OP_MAP_OUT = range(8)
 MAX_PARTS = 64
 INPUT_NHWC8, INPUT_S2D_ROW4, INPUT_S2D_ROW2, INPUT_S2D16 = 0, 1, 2, 3
 
@@ -34,6 +34,8 @@ SIGNATURES = {
     "semdiff_plan_set_conv_impl": (_I, [_P, _I]),
     "semdiff_workspace_bytes": (_L, [_P, _I, _I, _I]),
     "semdiff_score": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P, _L, _P, _P, _P, _P]),
+    "semdiff_score_map": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _L, _P, _P]),
+    "semdiff_decoder_op": (_I, [_I, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "semdiff_plan_set_profiling": (_I, [_P, _I]),
     "semdiff_plan_get_profile": (_I, [_P, C.POINTER(C.c_float), C.POINTER(_I), _I, _I]),
     "semdiff_plan_last_launches": (_L, [_P]),

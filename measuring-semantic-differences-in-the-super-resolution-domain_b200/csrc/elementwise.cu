@@ -483,4 +483,182 @@ int launch_avgpool(const void* in, void* out, int n, int H, int W, int C, int wi
   return SEMDIFF_ERR_ARG;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Local-map decoder helpers (the reference's U-Net over squared feature differences,
+// /root/reference/models/local_eval_models.py:109-125): (a - b)^2 tensors, channel concat, bilinear x2
+// upsampling with align_corners = True (nn.UpsamplingBilinear2d, :84), final upsample + sigmoid.
+// ---------------------------------------------------------------------------------------------
+// 8 logical channels <-> stored representation, any precision: T = fp32 (plain), 16-bit (plain) or 16-bit split
+template <typename T, bool kSplit> struct Val8 {
+  // logical 8-channel chunk i of a tensor whose pixels hold C logical channels (C % 64 == 0 when split)
+  static __device__ __forceinline__ int64_t offset(int64_t i) { return kSplit ? (i >> 3) * 128 + (i & 7) * 8 : i * 8; }
+  static __device__ __forceinline__ void load(const T* base, int64_t i, float (&f)[8]) {
+    const T* p = base + offset(i);
+    Vec8<T>::load(p, f);
+    if constexpr (kSplit) {
+      float l[8];
+      Vec8<T>::load(p + 64, l);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += l[k];
+    }
+  }
+  static __device__ __forceinline__ void store(T* base, int64_t i, const float (&f)[8]) {
+    T* p = base + offset(i);
+    if constexpr (kSplit) {
+      const uint4 qh = pack8<T>(f);
+      float h[8];
+      unpack8<T>(qh, h);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) h[k] = f[k] - h[k];
+      *reinterpret_cast<uint4*>(p) = qh;
+      *reinterpret_cast<uint4*>(p + 64) = pack8<T>(h);
+    } else {
+      Vec8<T>::store(p, f);
+    }
+  }
+};
+
+// in = [2n, HW, C] (GT images first) -> out[n, HW, C] = (gt - sr)^2; chunks = n * HW * C / 8
+template <typename T, bool kSplit>
+__global__ void __launch_bounds__(256) sqdiff_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t chunks) {
+  pdl_trigger();
+  pdl_wait();
+  const T* b = in + chunks * 8 * (kSplit ? 2 : 1);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < chunks; i += (int64_t)gridDim.x * blockDim.x) {
+    float d[8];
+    if constexpr (kSplit) {   // (a_hi - b_hi) + (a_lo - b_lo): the hi difference is exact for nearby values
+      const int64_t o = Val8<T, true>::offset(i);
+      float ah[8], al[8], bh[8], bl[8];
+      Vec8<T>::load(in + o, ah); Vec8<T>::load(in + o + 64, al); Vec8<T>::load(b + o, bh); Vec8<T>::load(b + o + 64, bl);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = (ah[k] - bh[k]) + (al[k] - bl[k]);
+    } else {
+      float fa[8], fb[8];
+      Val8<T, false>::load(in, i, fa);
+      Val8<T, false>::load(b, i, fb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[k] = fa[k] - fb[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] *= d[k];
+    Val8<T, kSplit>::store(out, i, d);
+  }
+}
+
+// channel concat of two NHWC tensors with q1 / q2 16-byte chunks per pixel (any element type / split storage)
+__global__ void __launch_bounds__(256) concat_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out,
+                                                     int64_t pixels, int q1, int q2) {
+  pdl_trigger();
+  pdl_wait();
+  const int q = q1 + q2;
+  const int64_t total = pixels * q;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / q;
+    const int c = (int)(i - p * q);
+    out[i] = c < q1 ? __ldg(a + p * q1 + c) : __ldg(b + p * q2 + (c - q1));
+  }
+}
+
+// torch's bilinear source index for align_corners = True: src = dst * (in - 1) / (out - 1), in fp32 like ATen
+struct Lerp { int i0, i1; float w0, w1; };
+__device__ __forceinline__ Lerp lerp_at(int o, int in_size, float scale) {
+  const float s = scale * (float)o;
+  int i0 = (int)s;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  const int i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+  const float w1 = s - (float)i0;
+  return Lerp{i0, i1, 1.f - w1, w1};
+}
+
+// nn.UpsamplingBilinear2d(scale_factor=2): [n, H, W, C] -> [n, 2H, 2W, C]
+template <typename T, bool kSplit>
+__global__ void __launch_bounds__(256) upsample2x_kernel(const T* __restrict__ in, T* __restrict__ out, int n_img, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int cv = C / 8, OH = 2 * H, OW = 2 * W;
+  const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f, sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  const int64_t total = (int64_t)n_img * OH * OW * cv;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    int64_t p = i / cv;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH);
+    const int64_t n = p / OH;
+    const Lerp ly = lerp_at(oy, H, sy), lx = lerp_at(ox, W, sx);
+    float v00[8], v01[8], v10[8], v11[8], r[8];
+    Val8<T, kSplit>::load(in, ((n * H + ly.i0) * W + lx.i0) * cv + c8, v00);
+    Val8<T, kSplit>::load(in, ((n * H + ly.i0) * W + lx.i1) * cv + c8, v01);
+    Val8<T, kSplit>::load(in, ((n * H + ly.i1) * W + lx.i0) * cv + c8, v10);
+    Val8<T, kSplit>::load(in, ((n * H + ly.i1) * W + lx.i1) * cv + c8, v11);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r[k] = ly.w0 * (lx.w0 * v00[k] + lx.w1 * v01[k]) + ly.w1 * (lx.w0 * v10[k] + lx.w1 * v11[k]);
+    Val8<T, kSplit>::store(out, i, r);
+  }
+}
+
+// final step of the decoder: channel 0 of [n, H, W, C] -> bilinear x2 -> sigmoid -> fp32 [n, 1, 2H, 2W]
+template <typename T, bool kSplit>
+__global__ void __launch_bounds__(256) map_out_kernel(const T* __restrict__ in, float* __restrict__ out, int n_img, int H, int W, int C) {
+  pdl_trigger();
+  pdl_wait();
+  const int OH = 2 * H, OW = 2 * W, CS = kSplit ? 2 * C : C;
+  const float sy = OH > 1 ? (float)(H - 1) / (float)(OH - 1) : 0.f, sx = OW > 1 ? (float)(W - 1) / (float)(OW - 1) : 0.f;
+  const int64_t total = (int64_t)n_img * OH * OW;
+  auto at = [&](int64_t n, int y, int x) {
+    const T* p = in + ((n * H + y) * W + x) * CS;
+    float v = Elem<T>::to_f(p[0]);
+    if constexpr (kSplit) v += Elem<T>::to_f(p[64]);
+    return v;
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t p = i;
+    const int ox = (int)(p % OW); p /= OW;
+    const int oy = (int)(p % OH);
+    const int64_t n = p / OH;
+    const Lerp ly = lerp_at(oy, H, sy), lx = lerp_at(ox, W, sx);
+    const float v = ly.w0 * (lx.w0 * at(n, ly.i0, lx.i0) + lx.w1 * at(n, ly.i0, lx.i1)) +
+                    ly.w1 * (lx.w0 * at(n, ly.i1, lx.i0) + lx.w1 * at(n, ly.i1, lx.i1));
+    out[i] = 1.f / (1.f + expf(-v));
+  }
+}
+
+template <typename T, bool kSplit>
+static int decoder_op_t(int what, const void* in, const void* in2, void* out, int n_img, int H, int W, int C, int C2, cudaStream_t st) {
+  const int64_t chunks = (int64_t)n_img * H * W * C / 8;
+  switch (what) {
+    case 0: launch_pdl(sqdiff_kernel<T, kSplit>, dim3(grid_for(chunks, 256)), dim3(256), 0, st, (const T*)in, (T*)out, chunks); break;
+    case 1: {
+      const int eb = (int)sizeof(T) * (kSplit ? 2 : 1);
+      const int64_t pixels = (int64_t)n_img * H * W;
+      launch_pdl(concat_kernel, dim3(grid_for(pixels * (C + C2) * eb / 16, 256)), dim3(256), 0, st, (const uint4*)in, (const uint4*)in2,
+                 (uint4*)out, pixels, C * eb / 16, C2 * eb / 16);
+      break;
+    }
+    case 2: launch_pdl(upsample2x_kernel<T, kSplit>, dim3(grid_for(chunks * 4, 256)), dim3(256), 0, st, (const T*)in, (T*)out, n_img, H, W, C); break;
+    case 3: launch_pdl(map_out_kernel<T, kSplit>, dim3(grid_for((int64_t)n_img * H * W * 4, 256)), dim3(256), 0, st, (const T*)in, (float*)out, n_img, H, W, C); break;
+  }
+  SEMDIFF_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// what: 0 = squared difference of the two halves of a stacked batch (n_img = PAIRS), 1 = channel concat (C | C2),
+// 2 = bilinear x2 upsampling, 3 = channel 0 -> bilinear x2 -> sigmoid -> fp32 map
+int launch_decoder_op(int what, const void* in, const void* in2, void* out, int n_img, int H, int W, int C, int C2, int precision,
+                      cudaStream_t st) {
+  if (n_img <= 0 || H <= 0 || W <= 0 || C <= 0 || C % 8 != 0 || (what == 1 && (C2 <= 0 || C2 % 8 != 0))) {
+    set_error("decoder op %d: bad shape n=%d %dx%dx%d (+%d)", what, n_img, H, W, C, C2);
+    return SEMDIFF_ERR_ARG;
+  }
+  if (is_split(precision) && (C % 64 != 0 || (what == 1 && C2 % 64 != 0))) { set_error("decoder op: split precisions need C %% 64 == 0"); return SEMDIFF_ERR_ARG; }
+  switch (precision) {
+    case SEMDIFF_BF16: return decoder_op_t<__nv_bfloat16, false>(what, in, in2, out, n_img, H, W, C, C2, st);
+    case SEMDIFF_FP16: return decoder_op_t<__half, false>(what, in, in2, out, n_img, H, W, C, C2, st);
+    case SEMDIFF_FP32: return decoder_op_t<float, false>(what, in, in2, out, n_img, H, W, C, C2, st);
+    case SEMDIFF_FP16X3: return decoder_op_t<__half, true>(what, in, in2, out, n_img, H, W, C, C2, st);
+    case SEMDIFF_BF16X3: return decoder_op_t<__nv_bfloat16, true>(what, in, in2, out, n_img, H, W, C, C2, st);
+  }
+  set_error("decoder op: bad precision %d", precision);
+  return SEMDIFF_ERR_ARG;
+}
+
 }  // namespace semdiff

@@ -54,6 +54,10 @@ int launch_pack(const void* gt, const void* sr, int in_precision, int n_pairs, i
 int launch_maxpool3x3s2(const void* in, void* out, int n_img, int H, int W, int c, int precision, cudaStream_t stream);
 int launch_avgpool(const void* in, void* out, int n_img, int H, int W, int c, int window, int precision,
                    cudaStream_t stream);
+// local-map decoder helpers (elementwise.cu): what = 0 squared difference of the GT / SR halves (n_img = pairs), 1 channel
+// concat (c | c2), 2 bilinear x2 upsampling (align_corners), 3 channel 0 -> bilinear x2 -> sigmoid -> fp32 map
+int launch_decoder_op(int what, const void* in, const void* in2, void* out, int n_img, int H, int W, int c, int c2, int precision,
+                      cudaStream_t stream);
 int launch_conv_simt(const ConvPtrs& ptr, const ConvShape& s, int precision, cudaStream_t stream);
 // tcgen05 path; use_tma lets the activation tile come through TMA (tiled for 1x1 stride 1, im2col mode otherwise);
 // false forces the cp.async software-im2col gather

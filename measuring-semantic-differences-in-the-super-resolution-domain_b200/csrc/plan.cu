@@ -29,7 +29,7 @@ bool pdl_enabled() {
   return on;
 }
 
-struct BufShape { int h = 0, w = 0, c = 0; };
+struct BufShape { int h = 0, w = 0, c = 0, pp = 2; };   // pp: images per pair held by the buffer (1 downstream of SQDIFF)
 struct Prepared;
 
 // everything that depends on (workspace address, images in the micro-batch, H, W)
@@ -41,6 +41,7 @@ struct ShapePlan {
   std::vector<int> impl;                       // per op: SEMDIFF_CONV_*
   std::vector<char> fused_away;                // per op: 1 = computed by the chained launch of an earlier op (conv_chain.cu)
   int chunk_imgs = 0;                          // images per head chunk (0 = head ops run on the whole micro-batch)
+  int map_h = 0, map_w = 0;                    // size of the output map (programs ending in SEMDIFF_OP_MAP_OUT)
   int64_t partial_offset = 0;
   int64_t total_bytes = 0;
   bool prepared = false;
@@ -54,6 +55,7 @@ using namespace semdiff;
 struct semdiff_plan {
   std::vector<semdiff_op> ops;
   int n_bufs = 0, precision = 0, n_taps = 0, conv_impl = SEMDIFF_CONV_AUTO, input_layout = SEMDIFF_INPUT_NHWC8;
+  bool has_map = false;   // the program ends in SEMDIFF_OP_MAP_OUT (local-map U-Net) instead of feeding TAP ops to the head
   // The first `head_ops` ops (stem + first pool) stream the widest activations of the trunk.  They run in chunks of
   // images small enough that pack output and stem output stay L2-resident between the three kernels (the buffers are
   // reused by every chunk, so the lines are overwritten in cache instead of travelling to HBM and back).
@@ -124,7 +126,7 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
         if (in.c != op.cin) { set_error("op %d: cin %d != buffer channels %d", i, op.cin, in.c); return SEMDIFF_ERR_ARG; }
         {
           const int ph = op.pad + (op.pad_hi < 0 ? op.pad : op.pad_hi);
-          out = BufShape{(in.h + ph - op.kh) / op.stride + 1, (in.w + ph - op.kw) / op.stride + 1, op.cout};
+          out = BufShape{(in.h + ph - op.kh) / op.stride + 1, (in.w + ph - op.kw) / op.stride + 1, op.cout, in.pp};
         }
         if (op.src2 >= 0) {
           if (op.src2 >= P->n_bufs || cur[op.src2].c == 0) { set_error("op %d: bad second source buffer", i); return SEMDIFF_ERR_ARG; }
@@ -145,9 +147,26 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
           }
         }
         break;
-      case SEMDIFF_OP_MAXPOOL3S2: out = BufShape{(in.h - 1) / 2 + 1, (in.w - 1) / 2 + 1, in.c}; break;
-      case SEMDIFF_OP_AVGPOOL: out = BufShape{in.h / op.stride, in.w / op.stride, in.c}; break;
+      case SEMDIFF_OP_MAXPOOL3S2: out = BufShape{(in.h - 1) / 2 + 1, (in.w - 1) / 2 + 1, in.c, in.pp}; break;
+      case SEMDIFF_OP_AVGPOOL: out = BufShape{in.h / op.stride, in.w / op.stride, in.c, in.pp}; break;
       case SEMDIFF_OP_TAP: continue;
+      case SEMDIFF_OP_SQDIFF:
+        if (in.pp != 2) { set_error("op %d: SQDIFF needs a buffer holding GT and SR images", i); return SEMDIFF_ERR_ARG; }
+        out = BufShape{in.h, in.w, in.c, 1};
+        break;
+      case SEMDIFF_OP_CONCAT: {
+        if (op.src2 < 0 || op.src2 >= P->n_bufs || cur[op.src2].c == 0) { set_error("op %d: bad second source buffer", i); return SEMDIFF_ERR_ARG; }
+        const BufShape b2 = cur[op.src2];
+        if (b2.h != in.h || b2.w != in.w || b2.pp != in.pp || op.dst == op.src2) { set_error("op %d: CONCAT of %dx%d and %dx%d tensors", i, in.h, in.w, b2.h, b2.w); return SEMDIFF_ERR_ARG; }
+        S->op_src2[i] = b2;
+        out = BufShape{in.h, in.w, in.c + b2.c, in.pp};
+        break;
+      }
+      case SEMDIFF_OP_UPSAMPLE2X: out = BufShape{2 * in.h, 2 * in.w, in.c, in.pp}; break;
+      case SEMDIFF_OP_MAP_OUT:
+        if (in.pp != 1) { set_error("op %d: MAP_OUT needs a one-image-per-pair buffer", i); return SEMDIFF_ERR_ARG; }
+        S->map_h = 2 * in.h; S->map_w = 2 * in.w;
+        continue;
       default: set_error("op %d: unknown kind %d", i, op.kind); return SEMDIFF_ERR_ARG;
     }
     if (out.h <= 0 || out.w <= 0) { set_error("op %d: empty output (input %dx%d too small)", i, in.h, in.w); return SEMDIFF_ERR_ARG; }
@@ -158,7 +177,7 @@ static int infer_shapes(const semdiff_plan* P, int pairs, int H, int W, ShapePla
     }
     S->op_dst[i] = out;
     cur[op.dst] = out;
-    const int64_t e = (i + 1 < P->head_ops ? head_img : n_img) * out.h * out.w * out.c;
+    const int64_t e = (i + 1 < P->head_ops ? head_img : (int64_t)pairs * out.pp) * out.h * out.w * out.c;
     if (e > buf_elems[op.dst]) buf_elems[op.dst] = e;
   }
   S->buf_offset.assign(P->n_bufs, 0);
@@ -217,7 +236,7 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
     if (op.kind != SEMDIFF_OP_CONV || S->fused_away[i]) continue;
     const bool in_head = chunk > 0 && i < P->head_ops;
     if (in_head && i + 1 == P->head_ops) { set_error("the last head op must be a pooling op"); return SEMDIFF_ERR_UNSUPPORTED; }
-    const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], in_head ? chunk : 2 * pairs);
+    const ConvShape cs = conv_shape(op, S->op_src[i], S->op_src2[i], in_head ? chunk : pairs * S->op_src[i].pp);
     const int impl = choose_impl(P, cs);
     if (impl < 0) {
       set_error("op %d: conv %dx%d cin=%d cout=%d stride=%d has no split-precision kernel (needs whole 64-channel blocks)", i, op.kh, op.kw,
@@ -235,7 +254,7 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
       bool dead = true;
       for (int j = i + 2; j < n_ops && dead; ++j) {
         const semdiff_op& o = P->ops[j];
-        if (o.src == op.dst || (o.kind == SEMDIFF_OP_CONV && (o.res == op.dst || o.src2 == op.dst))) dead = false;
+        if (o.src == op.dst || ((o.kind == SEMDIFF_OP_CONV || o.kind == SEMDIFF_OP_CONCAT) && (o.res == op.dst || o.src2 == op.dst))) dead = false;
         else if (o.kind != SEMDIFF_OP_TAP && o.dst == op.dst) break;   // overwritten before any read
       }
       if (dead) {
@@ -254,7 +273,7 @@ static int prepare(semdiff_plan* P, ShapePlan* S, int pairs, char* ws) {
       while (j < n_ops && P->ops[j].kind == SEMDIFF_OP_TAP) ++j;
       if (j < n_ops && P->ops[j].kind == SEMDIFF_OP_CONV && P->ops[j].src == op.dst && P->ops[j].res < 0 && P->ops[j].src2 < 0 &&
           P->ops[j].dst != op.src && P->ops[j].dst != op.res && P->ops[j].dst != op.src2 && P->ops[j].dst != op.dst) {
-        const ConvShape c2 = conv_shape(P->ops[j], S->op_src[j], S->op_src2[j], 2 * pairs);
+        const ConvShape c2 = conv_shape(P->ops[j], S->op_src[j], S->op_src2[j], pairs * S->op_src[j].pp);
         if (conv_chain_supported(cs, c2, op.res >= 0, P->precision)) {
           int rc = conv_chain_prepare(&S->tc[i], conv_ptrs(op, *S, ws), cs, conv_ptrs(P->ops[j], *S, ws), c2, P->precision);
           if (rc != 0) return rc;
@@ -316,9 +335,16 @@ int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, in
   P->ops.assign(ops, ops + n_ops);
   P->n_bufs = n_bufs;
   P->precision = precision;
-  for (const semdiff_op& op : P->ops)
+  for (const semdiff_op& op : P->ops) {
     if (op.kind == SEMDIFF_OP_TAP && op.tap + 1 > P->n_taps) P->n_taps = op.tap + 1;
-  if (P->n_taps < 1 || P->n_taps > 16) {
+    if (op.kind == SEMDIFF_OP_MAP_OUT) P->has_map = true;
+  }
+  if (P->has_map && (P->n_taps != 0 || P->ops.back().kind != SEMDIFF_OP_MAP_OUT)) {
+    set_error("plan_create: a map program ends in its single MAP_OUT op and has no TAP ops");
+    delete P;
+    return SEMDIFF_ERR_ARG;
+  }
+  if (!P->has_map && (P->n_taps < 1 || P->n_taps > 16)) {
     set_error("plan_create: need 1..16 TAP ops, got %d", P->n_taps);
     delete P;
     return SEMDIFF_ERR_ARG;
@@ -397,13 +423,11 @@ int semdiff_plan_get_profile(semdiff_plan* P, float* out_ms, int32_t* out_launch
 
 int64_t semdiff_plan_last_launches(const semdiff_plan* P) { return P ? P->last_launches : -1; }
 
-int semdiff_score(semdiff_plan* P, const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H,
-                  int32_t W, int32_t mb, const float* head_w, const float* head_b, int32_t normalize, void* workspace,
-                  int64_t workspace_bytes, float* out_scores, float* out_pre_relu, float* out_chan_mean,
-                  semdiff_stream_t stream_) {
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
-  if (P == nullptr || gt == nullptr || sr == nullptr || head_w == nullptr || head_b == nullptr || workspace == nullptr ||
-      out_scores == nullptr) { set_error("score: null argument"); return SEMDIFF_ERR_ARG; }
+// the executor behind semdiff_score (programs with TAP ops -> head) and semdiff_score_map (programs ending in MAP_OUT)
+static int run_program(semdiff_plan* P, const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H,
+                       int32_t W, int32_t mb, const float* head_w, const float* head_b, int32_t normalize, void* workspace,
+                       int64_t workspace_bytes, float* out_scores, float* out_pre_relu, float* out_chan_mean, float* out_map,
+                       cudaStream_t st) {
   if (n_pairs < 0 || H <= 0 || W <= 0 || mb <= 0) { set_error("score: bad sizes"); return SEMDIFF_ERR_ARG; }
   if (in_precision < SEMDIFF_BF16 || in_precision > SEMDIFF_FP32) { set_error("score: bad input precision %d", in_precision); return SEMDIFF_ERR_ARG; }
   P->last_launches = 0;
@@ -453,20 +477,30 @@ int semdiff_score(semdiff_plan* P, const void* gt, const void* sr, int32_t in_pr
         return rc;
       }
       ProfScope ps(P, i, st);
+      if (op.kind == SEMDIFF_OP_MAP_OUT) {
+        P->last_launches++;
+        return launch_decoder_op(3, src, nullptr, out_map + (int64_t)p0 * S.map_h * S.map_w, cur, in.h, in.w, in.c, 0, P->precision, st);
+      }
       const BufShape o = S.op_dst[i];
       char* dst = ws + S.buf_offset[op.dst] + (int64_t)dst_img0 * o.h * o.w * o.c * (int64_t)elem_bytes(P->precision);
+      if (op.kind >= SEMDIFF_OP_SQDIFF) {
+        const char* src2 = op.kind == SEMDIFF_OP_CONCAT ? ws + S.buf_offset[op.src2] : nullptr;
+        P->last_launches++;
+        return launch_decoder_op(op.kind - SEMDIFF_OP_SQDIFF, src, src2, dst, cur * o.pp, in.h, in.w, in.c,
+                                 op.kind == SEMDIFF_OP_CONCAT ? S.op_src2[i].c : 0, P->precision, st);
+      }
       if (op.kind == SEMDIFF_OP_CONV) {
         if (S.impl[i] == SEMDIFF_CONV_SIMT) {
           ConvPtrs q = conv_ptrs(op, S, ws);
           q.out = dst;
-          rc = launch_conv_simt(q, conv_shape(op, in, S.op_src2[i], imgs), P->precision, st);
+          rc = launch_conv_simt(q, conv_shape(op, in, S.op_src2[i], in.pp == 2 ? imgs : cur), P->precision, st);
         } else {
           rc = conv_tc_launch(tail_launch ? &S.tc_tail[i] : &S.tc[i], st);
         }
       } else if (op.kind == SEMDIFF_OP_MAXPOOL3S2) {
-        rc = launch_maxpool3x3s2(src, dst, imgs, in.h, in.w, in.c, P->precision, st);
+        rc = launch_maxpool3x3s2(src, dst, in.pp == 2 ? imgs : cur, in.h, in.w, in.c, P->precision, st);
       } else {
-        rc = launch_avgpool(src, dst, imgs, in.h, in.w, in.c, op.stride, P->precision, st);
+        rc = launch_avgpool(src, dst, in.pp == 2 ? imgs : cur, in.h, in.w, in.c, op.stride, P->precision, st);
       }
       P->last_launches++;
       return rc;
@@ -498,7 +532,7 @@ int semdiff_score(semdiff_plan* P, const void* gt, const void* sr, int32_t in_pr
       int rc = run_op(i, n_img, 0, false);
       if (rc != 0) return rc;
     }
-    {
+    if (!P->has_map) {
       ProfScope ps(P, n_ops + 2, st);
       int rc = launch_head(partials, P->n_taps, cur, tap_parts, tap_hw, head_b, out_scores + p0,
                            out_pre_relu ? out_pre_relu + p0 : nullptr, st);
@@ -507,6 +541,31 @@ int semdiff_score(semdiff_plan* P, const void* gt, const void* sr, int32_t in_pr
     }
   }
   return 0;
+}
+
+int semdiff_score(semdiff_plan* P, const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H,
+                  int32_t W, int32_t mb, const float* head_w, const float* head_b, int32_t normalize, void* workspace,
+                  int64_t workspace_bytes, float* out_scores, float* out_pre_relu, float* out_chan_mean,
+                  semdiff_stream_t stream_) {
+  if (P == nullptr || gt == nullptr || sr == nullptr || head_w == nullptr || head_b == nullptr || workspace == nullptr ||
+      out_scores == nullptr) { set_error("score: null argument"); return SEMDIFF_ERR_ARG; }
+  if (P->has_map) { set_error("score: this plan produces a map (use semdiff_score_map)"); return SEMDIFF_ERR_ARG; }
+  return run_program(P, gt, sr, in_precision, n_pairs, H, W, mb, head_w, head_b, normalize, workspace, workspace_bytes, out_scores,
+                     out_pre_relu, out_chan_mean, nullptr, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+int semdiff_score_map(semdiff_plan* P, const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H, int32_t W,
+                      int32_t mb, void* workspace, int64_t workspace_bytes, float* out_map, semdiff_stream_t stream_) {
+  if (P == nullptr || gt == nullptr || sr == nullptr || workspace == nullptr || out_map == nullptr) { set_error("score_map: null argument"); return SEMDIFF_ERR_ARG; }
+  if (!P->has_map) { set_error("score_map: this plan has no MAP_OUT op (use semdiff_score)"); return SEMDIFF_ERR_ARG; }
+  return run_program(P, gt, sr, in_precision, n_pairs, H, W, mb, nullptr, nullptr, 0, workspace, workspace_bytes, nullptr, nullptr,
+                     nullptr, out_map, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+int semdiff_decoder_op(int32_t what, const void* in, const void* in2, void* out, int32_t n_img, int32_t H, int32_t W, int32_t c,
+                       int32_t c2, int32_t precision, semdiff_stream_t st) {
+  if (what < 0 || what > 3 || in == nullptr || out == nullptr || (what == 1 && in2 == nullptr)) { set_error("decoder_op: bad arguments"); return SEMDIFF_ERR_ARG; }
+  return launch_decoder_op(what, in, in2, out, n_img, H, W, c, c2, precision, reinterpret_cast<cudaStream_t>(st));
 }
 
 int semdiff_pack_input(const void* gt, const void* sr, int32_t in_precision, int32_t n_pairs, int32_t H, int32_t W,

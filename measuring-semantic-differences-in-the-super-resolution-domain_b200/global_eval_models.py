@@ -40,12 +40,12 @@ class _Plan:
     """Device-resident folded weights + the native plan handle.  Rebuilt when trunk weights change."""
 
     def __init__(self, clip: nn.Module, family: str, depth: int, precision: str, device: torch.device,
-                 s2d_stem: bool = True, lower_kwargs: dict | None = None):
+                 s2d_stem: bool = True, lower_kwargs: dict | None = None, program=None):
         self.lib = _lib.load()
         self.precision = _lib.PRECISIONS[precision]
         split = precision in _lib.SPLIT
         dt = {"bf16": torch.bfloat16, "fp16": torch.float16, "fp32": torch.float32}[_lib.SPLIT.get(precision, precision)]
-        self.program = trunks.LOWER[family](clip, depth, s2d_stem, **(lower_kwargs or {}))
+        self.program = program or trunks.LOWER[family](clip, depth, s2d_stem, **(lower_kwargs or {}))
         ops = self.program.ops
         self._keep = []
         arr = (_lib.SemdiffOp * len(ops))()

@@ -177,16 +177,22 @@ def create_trunk(clip_name: str, seed: int = 0, pretrained: bool | None = None) 
 # lowering: module tree -> op list with folded weights
 # ---------------------------------------------------------------------------------------------
 
-def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d, cin_pad: int | None = None):
-    """conv (no bias) followed by eval-mode BatchNorm -> (weight [Cout,KH,KW,Cin_pad] fp64, bias [Cout] fp64)."""
+def fold_conv_bn(conv: nn.Conv2d, bn: nn.BatchNorm2d | None, cin_pad: int | None = None):
+    """conv (with or without bias) followed by eval-mode BatchNorm (or by nothing: bn=None)
+    -> (weight [Cout,KH,KW,Cin_pad] fp64, bias [Cout] fp64)."""
     w = conv.weight.detach().double().cpu()
-    gamma, beta = bn.weight.detach().double().cpu(), bn.bias.detach().double().cpu()
-    mean, var = bn.running_mean.detach().double().cpu(), bn.running_var.detach().double().cpu()
-    scale = gamma / torch.sqrt(var + bn.eps)
+    cb = conv.bias.detach().double().cpu() if conv.bias is not None else torch.zeros(w.shape[0], dtype=torch.float64)
+    if bn is None:
+        scale, shift = torch.ones(w.shape[0], dtype=torch.float64), cb
+    else:
+        gamma, beta = bn.weight.detach().double().cpu(), bn.bias.detach().double().cpu()
+        mean, var = bn.running_mean.detach().double().cpu(), bn.running_var.detach().double().cpu()
+        scale = gamma / torch.sqrt(var + bn.eps)
+        shift = beta + (cb - mean) * scale
     w = (w * scale[:, None, None, None]).permute(0, 2, 3, 1).contiguous()
     if cin_pad is not None and cin_pad > w.shape[-1]:
         w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
-    return w, beta - mean * scale
+    return w, shift
 
 
 def split_weight(w: torch.Tensor, dt16: torch.dtype):
@@ -213,6 +219,7 @@ class Program:
         self.n_bufs = 0
         self.input_layout = _lib.INPUT_NHWC8
         self.head_ops = 0   # leading ops (stem + first pool) the plan may run in L2-sized image chunks
+        self.sqdiff_bufs = None   # local-map programs: tap j becomes a SQDIFF op into buffer sqdiff_bufs[j] (see tap())
 
     def conv(self, conv, bn, src, dst, res=-1, relu=True, cin_pad=None, second=None, cout_pad=None):
         """One fused conv+BN(+ReLU) op.  `second=(conv1x1, bn, src2)` folds a projection shortcut into the same
@@ -222,8 +229,9 @@ class Program:
         if cout_pad is not None and cout_pad > w.shape[0]:   # zero filters: the extra output channels are exactly 0
             w = torch.cat([w, torch.zeros(cout_pad - w.shape[0], *w.shape[1:], dtype=w.dtype)])
             b = torch.cat([b, torch.zeros(cout_pad - b.shape[0], dtype=b.dtype)])
+        pad = conv.padding[0] if not isinstance(conv.padding, str) else {"same": conv.kernel_size[0] // 2, "valid": 0}[conv.padding]
         op = dict(kind=_lib.OP_CONV, src=src, dst=dst, res=res, cin=w.shape[3], cout=w.shape[0],
-                  kh=w.shape[1], kw=w.shape[2], stride=conv.stride[0], pad=conv.padding[0],
+                  kh=w.shape[1], kw=w.shape[2], stride=conv.stride[0], pad=pad,
                   relu=int(relu), tap=-1, src2=-1, cin2=0, stride2=1, pad_hi=-1,
                   alg_k=conv.in_channels * conv.kernel_size[0] * conv.kernel_size[1], alg_cout=conv.out_channels,
                   n_convs=1)
@@ -270,7 +278,14 @@ class Program:
         self.ops.append(dict(kind=kind, src=src, dst=dst, res=-1, cin=0, cout=0, kh=window, kw=window, stride=window,
                              pad=0, relu=0, tap=-1, src2=-1, cin2=0, stride2=1, pad_hi=-1, w=None, b=None))
 
+    def simple(self, kind, src, dst, src2=-1):
+        """SQDIFF / CONCAT / UPSAMPLE2X / MAP_OUT (include/semdiff_b200.h)"""
+        self.ops.append(dict(kind=kind, src=src, dst=dst, res=-1, cin=0, cout=0, kh=0, kw=0, stride=0, pad=0, relu=0, tap=-1,
+                             src2=src2, cin2=0, stride2=1, pad_hi=-1, w=None, b=None))
+
     def tap(self, src, j):
+        if self.sqdiff_bufs is not None:     # local maps: the decoder consumes (a - b)^2 of the tapped activation
+            return self.simple(_lib.OP_SQDIFF, src, self.sqdiff_bufs[j])
         self.ops.append(dict(kind=_lib.OP_TAP, src=src, dst=-1, res=-1, cin=0, cout=0, kh=0, kw=0, stride=0, pad=0,
                              relu=0, tap=j, src2=-1, cin2=0, stride2=1, pad_hi=-1, w=None, b=None))
 
@@ -304,15 +319,26 @@ class Program:
         self.input_layout = _lib.INPUT_S2D16
 
 
-def lower_resnet50(clip: nn.Module, depth: int, s2d_stem=True) -> Program:
+def lower_resnet50(clip: nn.Module, depth: int, s2d_stem=True, program: Program | None = None, raw_stem_tap: bool = False) -> Program:
     """timm resnet50; taps = layer{s}.2.act3 for s in range(4-depth, 5)  (global_eval_models.py:701).
     s2d_stem: "s2d16" (16-bit modes, stem output width <= 125: strip kernel over the compact space-to-depth input),
     True / "row4" (row-window layout, generic im2col path: any even size, fp32 mode), False (channel-padded 7x7 conv
     through the gather producer: odd image sizes)."""
-    P = Program()
+    P = program or Program()
     IN, A, B, T1, T2 = range(5)
-    P.n_bufs = 5
+    P.n_bufs = max(P.n_bufs, 5)
     c1 = clip.conv1
+    first_tap = 0
+    if raw_stem_tap:
+        # the local-map U-Net hooks the module `conv1` itself (/root/reference/models/local_eval_models.py:196): the raw
+        # 7x7 conv output before bn1 / act1 - one more stem launch with the un-folded weights
+        if s2d_stem and c1.kernel_size == (7, 7) and c1.stride == (2, 2):
+            P.stem7_s2d(c1, None, IN, T2)
+            P.ops[-1]["relu"] = 0
+        else:
+            P.conv(c1, None, IN, T2, cin_pad=8, relu=False)
+        P.tap(T2, 0)
+        first_tap = 1
     if s2d_stem and c1.kernel_size == (7, 7) and c1.stride == (2, 2) and c1.padding == (3, 3) and c1.in_channels == 3:
         if s2d_stem == "s2d16" and c1.out_channels == 64:
             P.stem7_s2d16(c1, clip.bn1, IN, T1)
@@ -337,18 +363,19 @@ def lower_resnet50(clip: nn.Module, depth: int, s2d_stem=True) -> Program:
                 P.conv(blk.conv3, blk.bn3, T2, y, res=x)
             x = y
             if bi == 2 and li >= 4 - depth:
-                P.tap(x, li - (4 - depth))
+                P.tap(x, first_tap + li - (4 - depth))
     return P
 
 
-def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True, taps: dict | None = None) -> Program:
+def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True, taps: dict | None = None,
+                        program: Program | None = None, stem_tap: bool = False) -> Program:
     """timm resnet50_clip.openai; taps = stages.{s}.2.act for s in range(3-depth, 4)  (global_eval_models.py:327),
     or an explicit {(stage, block): tap index} map (CLIP_lpips_wperlay_cnn, :832-833)."""
     if taps is None:
-        taps = {(s, 2): s - (3 - depth) for s in range(3 - depth, 4)}
-    P = Program()
+        taps = {(s, 2): s - (3 - depth) + (1 if stem_tap else 0) for s in range(3 - depth, 4)}
+    P = program or Program()
     IN, A, B, T1, T2, T3, D0 = range(7)
-    P.n_bufs = 7
+    P.n_bufs = max(P.n_bufs, 7)
     st = clip.stem
     c1 = st.conv1.conv
     if s2d_stem and c1.kernel_size == (3, 3) and c1.stride == (2, 2) and c1.padding == (1, 1) and c1.in_channels == 3:
@@ -368,8 +395,10 @@ def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True, taps
         P.conv(c1, st.conv1.bn, IN, T1, cin_pad=8)
         P.conv(st.conv2.conv, st.conv2.bn, T1, T2)
         P.conv(st.conv3.conv, st.conv3.bn, T2, T1)
+    if stem_tap:   # `stem.conv3` (conv + bn + act, before stem.pool): the local-map U-Net's first tap (local_eval_models.py:27)
+        P.tap(T1, 0)
     P.pool(_lib.OP_AVGPOOL, T1, A, 2)
-    P.head_ops = len(P.ops)
+    P.head_ops = len(P.ops) if not stem_tap else 0
     x = A
     for si, stage in enumerate(clip.stages.children()):
         for bi, blk in enumerate(stage.children()):
@@ -393,6 +422,40 @@ def lower_clip_resnet50(clip: nn.Module, depth: int, s2d_stem: bool = True, taps
             x = y
             if (si, bi) in taps:
                 P.tap(x, taps[(si, bi)])
+    return P
+
+
+def lower_unet(clip: nn.Module, decoder: nn.ModuleList, family: str, s2d_stem=True) -> Program:
+    """The local-map model of /root/reference/models/local_eval_models.py:7-171 (CLIP trunk) / :175-339 (ImageNet trunk):
+    trunk with five taps (stem + block 2 of every stage) -> (a - b)^2 per tap (:115) -> U-Net decoder (:117-123: two 3x3
+    conv + BN + ReLU per level, bilinear x2 upsampling, channel concat with the next shallower difference) -> sigmoid.
+    BatchNorm (eval mode) and the conv biases are folded; the 1-channel head conv is carried with 64 output channels."""
+    P = Program()
+    n_trunk = 5 if family == "resnet50" else 7
+    D = [n_trunk + j for j in range(5)]               # squared differences, shallow -> deep
+    U, CAT, X1, X2 = (n_trunk + 5 + j for j in range(4))
+    P.n_bufs = n_trunk + 9
+    P.sqdiff_bufs = D
+    if family == "resnet50":
+        lower_resnet50(clip, 3, s2d_stem, program=P, raw_stem_tap=True)
+    else:
+        lower_clip_resnet50(clip, 3, s2d_stem, program=P, stem_tap=True)
+    P.head_ops = 0
+    levels = list(decoder.children())
+    assert len(levels) == 5
+    def two_convs(seq, src):
+        m = list(seq.children())
+        P.conv(m[0], m[1], src, X1)
+        if isinstance(m[4], nn.BatchNorm2d):         # conv, bn, relu, conv, bn, relu
+            P.conv(m[3], m[4], X1, X2)
+        else:                                         # level 0: conv, bn, relu, conv 64 -> 1 (bias), relu
+            P.conv(m[3], None, X1, X2, cout_pad=64)
+    two_convs(levels[4], D[4])
+    for j in (3, 2, 1, 0):
+        P.simple(_lib.OP_UPSAMPLE2X, X2, U)
+        P.simple(_lib.OP_CONCAT, D[j], CAT, src2=U)   # torch.concat((diff[-j], bottom_pass), dim=1)  (:121)
+        two_convs(levels[j], CAT)
+    P.simple(_lib.OP_MAP_OUT, X2, -1)                 # upscaler + final_sigmoid (:123-125)
     return P
 
 

@@ -66,5 +66,32 @@ def main():
     print("wrote", OUT)
 
 
+UNET_OUT = os.path.join(os.path.dirname(OUT), "unet_goldens.json")
+
+
+def main_unet():
+    """tests/golden/unet_goldens.json: the reference's local-map U-Nets (local_eval_models.py:7-339, executed verbatim via
+    reference_loader.build_reference_unet) on seeded pairs, decoder calibrated by restated.calibrate_unet_decoder.  The
+    224x224 maps are stored on a 16-pixel grid (196 values per pair)."""
+    from oracle.restated import calibrate_unet_decoder
+
+    torch.set_num_threads(os.cpu_count())
+    records = []
+    for trunk in ("resnet50", "resnet50_clip.openai"):
+        model = calibrate_unet_decoder(rl.build_reference_unet(trunk, seed=0))
+        gt, sr = make_pairs(2, seed=5)
+        with torch.no_grad():
+            m = model(gt, sr)
+        records.append({"trunk": trunk, "n_pairs": 2, "input_seed": 5, "weight_seed": 0, "shape": list(m.shape),
+                        "grid": 16, "map": [[float(v) for v in row] for row in m[:, 0, 8::16, 8::16].reshape(2, -1)],
+                        "mean": float(m.mean()), "state_dict_keys": len(model.state_dict())})
+        print(trunk, records[-1]["mean"], flush=True)
+    meta = {"generator": "oracle/make_goldens.py unet", "torch": torch.__version__, "reference_file": rl.REFERENCE_LOCAL_FILE,
+            "note": "outputs of the reference file's first two classes (lines 1-339, executed verbatim) through oracle/timm_shim"}
+    with open(UNET_OUT, "w") as f:
+        json.dump({"meta": meta, "records": records}, f, indent=1)
+    print("wrote", UNET_OUT)
+
+
 if __name__ == "__main__":
-    main()
+    main_unet() if "unet" in sys.argv[1:] else main()

@@ -228,3 +228,35 @@ def test_random_init_trunk_is_an_explicit_opt_in(monkeypatch):
     delattr(getattr(tree.layer1, "0"), "conv1")
     with pytest.raises(RuntimeError, match="1 missing"):
         trunks.check_trunk_keys(tree, "resnet50")
+
+
+@pytest.mark.parametrize("name", ["resnet50", "resnet50_clip.openai"])
+def test_unet_lowering_is_a_valid_map_program(name):
+    """The local-map program (trunk + five SQDIFF taps + decoder) passes the C-ABI's host-side shape inference: buffer
+    shapes chain, the map comes out at the input size, and score / score_map refuse each other's plans."""
+    import ctypes as C
+
+    from semdiff_b200.local_eval_models import _decoder
+    tree, dec = trunks.create_trunk(name), _decoder()
+    prog = trunks.lower_unet(tree, dec, name)
+    kinds = [op["kind"] for op in prog.ops]
+    assert kinds.count(_lib.OP_SQDIFF) == 5 and kinds.count(_lib.OP_CONCAT) == 4 and kinds.count(_lib.OP_UPSAMPLE2X) == 4
+    assert kinds[-1] == _lib.OP_MAP_OUT and _lib.OP_TAP not in kinds
+    dec_convs = [op for op in prog.ops if op["kind"] == _lib.OP_CONV][-10:]
+    assert [(op["cin"], op["cout"]) for op in dec_convs] == [(2048, 2048), (2048, 2048), (3072, 1024), (1024, 1024), (1536, 512),
+                                                               (512, 512), (768, 256), (256, 256), (320, 64), (64, 64)]
+    arr = (_lib.SemdiffOp * len(prog.ops))()
+    for i, op in enumerate(prog.ops):
+        arr[i] = _lib.SemdiffOp(op["kind"], op["src"], op["dst"], op["res"], op["cin"], op["cout"], op["kh"], op["kw"], op["stride"],
+                                op["pad"], op["relu"], op["tap"], op["src2"], op["cin2"], op["stride2"], op["pad_hi"], None, None, 1.0, 0)
+    lib = _lib.load()
+    handle = C.c_void_p()
+    for precision in (_lib.BF16, _lib.FP16X3):
+        assert lib.semdiff_plan_create(arr, len(prog.ops), prog.n_bufs, precision, prog.input_layout, 0, C.byref(handle)) == 0, lib.semdiff_last_error()
+        need = lib.semdiff_workspace_bytes(handle, 4, 224, 224)
+        assert need > 0, lib.semdiff_last_error()
+        assert lib.semdiff_workspace_bytes(handle, 4, 224, 224) < lib.semdiff_workspace_bytes(handle, 8, 224, 224)
+        one = C.c_void_p(16)
+        assert lib.semdiff_score(handle, one, one, _lib.FP32, 1, 224, 224, 1, one, one, 0, one, 16, one, None, None, None) == -1
+        assert b"semdiff_score_map" in lib.semdiff_last_error()
+        lib.semdiff_plan_destroy(handle)

@@ -107,3 +107,38 @@ def test_imagenet_oracle_trunk_is_torchvision_resnet50():
         assert len(got) == 4
         for a, b in zip(got, want):
             assert torch.equal(a, b), name
+
+
+# ---- local maps: /root/reference/models/local_eval_models.py:7-339 ----
+UNET_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "unet_goldens.json")
+
+
+@pytest.mark.skipif(not os.path.isfile(rl.REFERENCE_LOCAL_FILE), reason="/root/reference not present on this host")
+@pytest.mark.parametrize("trunk", ["resnet50", "resnet50_clip.openai"])
+def test_restated_unet_equals_reference_file(trunk):
+    from oracle.restated import RestatedUnet, calibrate_unet_decoder, unet_tap_names
+    ref = calibrate_unet_decoder(rl.build_reference_unet(trunk, seed=0))
+    mine = calibrate_unet_decoder(RestatedUnet(trunk, seed=0))
+    assert list(ref.state_dict().keys()) == list(mine.state_dict().keys())
+    for k, v in ref.state_dict().items():
+        assert torch.equal(v, mine.state_dict()[k]), k
+    assert ref.wanted_layers == mine.wanted_layers == unet_tap_names(trunk)
+    gt, sr = make_pairs(1, seed=9)
+    with torch.no_grad():
+        a, b = ref(gt, sr), mine(gt, sr)
+    assert a.shape == (1, 1, 224, 224) and torch.equal(a, b)
+
+
+def test_restated_unet_reproduces_goldens():
+    from oracle.restated import RestatedUnet, calibrate_unet_decoder
+    with open(UNET_GOLDEN) as f:
+        records = json.load(f)["records"]
+    assert {r["trunk"] for r in records} == {"resnet50", "resnet50_clip.openai"}
+    rec = records[0]   # one trunk keeps the CPU suite short; the GPU suite checks both
+    model = calibrate_unet_decoder(RestatedUnet(rec["trunk"], seed=rec["weight_seed"]))
+    gt, sr = make_pairs(rec["n_pairs"], seed=rec["input_seed"])
+    m = model(gt, sr)
+    assert list(m.shape) == rec["shape"] and len(model.state_dict()) == rec["state_dict_keys"]
+    got = m[:, 0, 8::16, 8::16].reshape(rec["n_pairs"], -1)
+    assert torch.allclose(got, torch.tensor(rec["map"]), rtol=0, atol=2e-5)
+    assert float(got.std()) > 0.01   # a real map, not a saturated constant
