@@ -48,7 +48,8 @@ def test_decoder_ops(precision):
     op(0, x, None, out, n, H, W, C, 0, precision)
     xv = value(x, precision)
     ref = (xv[:n] - xv[n:]) ** 2
-    assert ((value(out, precision) - ref).abs() <= tol * ref.abs() + 1e-30).all()
+    # fp16 halves: full 22-bit resolution for d^2 in [6.1e-5, 6.5e4]; below, the fp16 subnormal spacing (6e-8) is the floor
+    assert ((value(out, precision) - ref).abs() <= tol * ref.abs() + (6e-8 if precision == "fp16x3" else 1e-30)).all()
     # channel concat (:121)
     y = store(torch.randn(n, H, W, C2, device=DEV, generator=g), precision)
     cat = torch.empty(n, H, W, (C + C2) * mult, dtype=DT[precision], device=DEV)
