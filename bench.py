@@ -642,13 +642,52 @@ def run_hires1024(args, ctx):
         print(json.dumps(result), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------
+# workload: unet (the local-map U-Net, /root/reference/models/local_eval_models.py:7-339)
+# ---------------------------------------------------------------------------------------------
+def run_unet(args, ctx):
+    """Local semantic-difference maps per second: 64 pairs of 224x224 per GPU per step (trunk 2 x 8.2 GFLOP + decoder
+    56 GFLOP per pair), device-resident inputs, no collective (maps stay on their rank)."""
+    torch = ctx.torch
+    import warnings
+
+    import semdiff_b200
+
+    n = args.pairs if args.pairs != 256 else 64
+    g = torch.Generator(device=ctx.dev).manual_seed(99 + ctx.rank)
+    gt = torch.randn(n, 3, H, W, device=ctx.dev, generator=g)
+    sr = gt + 0.1 * torch.randn(n, 3, H, W, device=ctx.dev, generator=g)
+    result = {"workload": "unet", "pairs_per_gpu": n, "n_gpus": ctx.world, "unit": "maps/s", "modes": {}}
+    for trunk, cls in (("resnet50", semdiff_b200.CLIP_lpips_Unet_clsbckbn), ("resnet50_clip.openai", semdiff_b200.CLIP_lpips_Unet)):
+        for mode in args.modes.split(","):
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                model = cls(trunk, str(ctx.dev), precision=mode).eval()
+
+            def step():
+                with torch.no_grad():
+                    return model(gt, sr)
+
+            for _ in range(3):
+                m = step()
+            steps = max(3, args.steps // 4)
+            ms = ctx.timed(step, steps) / steps
+            result["modes"][f"{trunk}/{mode}"] = {"ms_per_step": ms, "maps_per_s": n * ctx.world / (ms / 1e3), "launches_per_step": model.plan().last_launches(),
+                                                   "tflops": (56.0e9 + (16.35e9 if trunk == "resnet50" else 21.47e9)) * n / (ms / 1e3) / 1e12,
+                                                   "map_mean": float(m.mean())}
+            del model
+            torch.cuda.empty_cache()
+    if ctx.rank == 0:
+        print(json.dumps(result), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="pairs224", help="pairs224 | sweep10k | hires1024, or a comma-separated list (one JSON line each)")
+    ap.add_argument("--workload", default="pairs224", help="pairs224 | sweep10k | hires1024 | unet, or a comma-separated list (one JSON line each)")
     ap.add_argument("--pairs", type=int, default=256, help="pairs per GPU per step (pairs224); total pairs (sweep10k: 10000, hires1024: 32)")
     ap.add_argument("--precision", default="bf16")
     ap.add_argument("--modes", default="fp16x3,bf16,fp16", help="sweep10k / hires1024: comma-separated precision modes (the first is the rank reference)")
@@ -667,7 +706,7 @@ def main():
     ctx = Ctx()
     try:
         for wl in args.workload.split(","):
-            {"pairs224": run_pairs224, "sweep10k": run_sweep10k, "hires1024": run_hires1024}[wl](args, ctx)
+            {"pairs224": run_pairs224, "sweep10k": run_sweep10k, "hires1024": run_hires1024, "unet": run_unet}[wl](args, ctx)
             ctx.torch.cuda.empty_cache()
     finally:
         ctx.close()
