@@ -562,9 +562,14 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   p.M = (int)s.M();
   p.m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
   p.num_kb = (s.K() + BLOCK_K - 1) / BLOCK_K;
-  // (split precisions: the 256-wide tile stages its output through one slot while the same warps must keep draining the next
-  // tile's chunk sums, which only amortises from K = 384 on - the same threshold, measured: profiles/r2_x3_per_op.txt)
-  const int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
+  int block_n = pick_block_n(s.cout, res != nullptr, p.num_kb, p.m_tiles, num_sms());
+  if (split && block_n == 256) {
+    // the 256-wide split tile stages its output through one slot while the same warps must keep draining the next tile's
+    // chunk sums, which only amortises over a long K loop: measured 15.19k / 15.31k / 15.41k pairs/s for a threshold of
+    // 6 / 8 / 10 K blocks (profiles/r2_x3_per_op.txt)
+    static const int min_kb = getenv("SEMDIFF_X3_N256_MIN_KB") ? atoi(getenv("SEMDIFF_X3_N256_MIN_KB")) : 10;
+    if (p.num_kb < min_kb) block_n = 128;
+  }
   if (block_n == 0) { set_error("conv_tc: cout %d not a multiple of 32", s.cout); return SEMDIFF_ERR_UNSUPPORTED; }
   p.in = in; p.bias = bias; p.has_res = res != nullptr;
   p.H = s.H; p.W = s.W; p.Cin = s.cin; p.OH = s.OH(); p.OW = s.OW(); p.Cout = s.cout;
