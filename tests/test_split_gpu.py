@@ -23,6 +23,9 @@ SPLIT_CONV_CASES = [
     (2, 14, 14, 1024, 256, 1, 1, 0, False),    # long K (48 ring fills per tile)
     (1, 9, 9, 64, 64, 3, 1, 1, False),         # tiny tensor (im2col descriptor workaround path)
     (2, 31, 16, 64, 64, 4, 1, 0, False),       # 4x4 pad-0 window (the ROW4 stem is 4x1)
+    (16, 56, 56, 64, 64, 3, 1, 1, False),      # 392 tiles on 148 CTAs: ring, TMEM-stage and C-ring counters wrap across tiles
+    (8, 56, 56, 128, 256, 1, 1, 0, True),      # 392 tiles x 2 n-tiles with residual prefetch across tile boundaries
+    (6, 28, 28, 1024, 256, 1, 1, 0, False),    # 256-wide tile (16 K blocks): 4 output groups through the single C slot
 ]
 
 
