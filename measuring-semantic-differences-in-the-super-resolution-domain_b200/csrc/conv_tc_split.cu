@@ -13,7 +13,7 @@
 //    that systematic shrink costs 1e-4 of the score.  So (1) within a K block the two small products are issued FIRST -
 //    while the accumulator only holds 2^-11-sized terms their truncation is free - and (2) the accumulation is PROMOTED:
 //    every `chunk_kb` K blocks (default 1 = 12 MMAs) the chunk sum is drained from TMEM and added in registers with
-//    round-to-nearest by the epilogue warps, while the next chunk accumulates from zero in the other TMEM stage.
+//    round-to-nearest by the epilogue warps, while the next chunks accumulate from zero in the other TMEM stages.
 //    Residual bias per conv: -9e-8; scores: <= 7e-6 of the fp32 oracle (tests/test_scorer_gpu.py).
 //  * an N = 128 SS-mode MMA reads 8 KB of operands per 64 tensor cycles = the whole shared-memory bandwidth, so the wide
 //    layers use 256-column tiles (12 KB per 128 cycles) and a ring fill is ONE K block = four tiles (A hi, A lo, W hi,
@@ -21,7 +21,7 @@
 //
 // CTA = one 128 x BLOCK_N tile at a time, persistent, warp-specialised like conv_tc.cu:
 //   warp 0     TMA producer (four tile loads per ring fill; tiled 2-D or im2col mode for A)
-//   warp 1     tcgen05.mma issuer; chunk c accumulates into TMEM stage (c & 1)
+//   warp 1     tcgen05.mma issuer; chunk c accumulates into TMEM stage c % ACC_STAGES (4 stages for tiles up to 128 wide)
 //   warps 2-9  drain + epilogue: warp (q, half) owns TMEM lanes 32q..32q+31 and, of every 64-column group, the 32 columns
 //              of its half; it sums the chunk accumulators in registers, then + bias (+ residual) -> ReLU -> split into
 //              hi / lo -> the group's two swizzled 64-column boxes
@@ -41,8 +41,9 @@ template <int BLOCK_N> struct SplitCfg {
   static constexpr int BOX_BYTES = BLOCK_M * 64 * 2;     // one 64-column 16-bit box of 128 rows
   static constexpr int GROUP_BYTES = 2 * BOX_BYTES;
   static constexpr int RING = BLOCK_N == 256 ? 1 : (BLOCK_N == 128 ? 3 : 2);
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;          // two accumulator stages
-  static constexpr int NUM_BARS = 2 * STAGES + 4 + 2 * RING;
+  static constexpr int ACC_STAGES = BLOCK_N == 256 ? 2 : 4;   // chunk accumulators in flight: the MMA warp runs this far ahead of the drain
+  static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;      // 256 / 512 / 512 columns
+  static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES + 2 * RING;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING * GROUP_BYTES + NUM_BARS * 8 + 16 + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
@@ -52,15 +53,15 @@ constexpr int SPLIT_THREADS = 11 * 32;
 template <typename T, int BLOCK_N, int kAMode>
 __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = SplitCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING, GROUPS = Cfg::GROUPS, EPI_WARPS = 8;
+  constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING, GROUPS = Cfg::GROUPS, EPI_WARPS = 8, ACC = Cfg::ACC_STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_c = smem + STAGES * Cfg::STAGE_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + RING * Cfg::GROUP_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* res_full_bar = tmem_empty_bar + 2;
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC;
+  uint64_t* res_full_bar = tmem_empty_bar + ACC;
   uint64_t* staged_bar = res_full_bar + RING;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(staged_bar + RING);
 
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const _
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ACC; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], EPI_WARPS);
     }
@@ -147,13 +148,13 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const _
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer: 12 MMAs per fill, small products first; chunk c -> TMEM stage c & 1 =====================
+    // ===================== MMA issuer: 12 MMAs per fill, small products first; chunk c -> TMEM stage c % ACC =====================
     constexpr uint32_t idesc = umma_idesc_f16(Elem<T>::kUmmaFormat, BLOCK_M, BLOCK_N);
     const uint64_t desc0 = umma_smem_desc_sw128(smem_u32(smem));
     int stage = 0, phase = 0, chunk = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.num_kb;) {
-        const int acc = chunk & 1, acc_phase = (chunk >> 1) & 1;
+        const int acc = chunk % ACC, acc_phase = (chunk / ACC) & 1;
         ++chunk;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -193,9 +194,9 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const _
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       float racc[GROUPS][32];
       for (int c = 0; c < n_chunks; ++c, ++chunk) {
-        const int acc = chunk & 1;
-        if (c == 0) mbar_wait_backoff(&tmem_full_bar[acc], (chunk >> 1) & 1);
-        else mbar_wait_short(&tmem_full_bar[acc], (chunk >> 1) & 1);
+        const int acc = chunk % ACC;
+        if (c == 0) mbar_wait_backoff(&tmem_full_bar[acc], (chunk / ACC) & 1);
+        else mbar_wait_short(&tmem_full_bar[acc], (chunk / ACC) & 1);
         tcgen05_fence_after();
 #pragma unroll
         for (int g = 0; g < GROUPS; ++g) {
