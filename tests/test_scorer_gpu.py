@@ -2,8 +2,10 @@
 (oracle/restated.py == the unmodified reference file, see test_oracle.py) on the same seeded inputs and weights,
 and against the committed golden vectors produced by the reference itself (tests/golden/).
 
-Tolerances (BASELINE.json north_star): fp32 mode 1e-5 relative; 16-bit modes are reported and bounded by what the
-storage type allows on random-init weights (1e-3 is not reachable with bf16 weights)."""
+Tolerances (BASELINE.json north_star): 1e-5 relative for the fp32 mode AND for the split-precision tensor-core mode
+(fp16x3, the module's default: well inside the 1e-3 the north_star asks of the tensor-core trunk); the plain 16-bit modes
+are reported and bounded by what their storage type allows on random-init weights (1e-3 is not reachable
+with bf16 activations - rounding every inter-layer tensor to 8 bits destroys (A-B)^2 on SR ~ GT pairs)."""
 import json
 import os
 
