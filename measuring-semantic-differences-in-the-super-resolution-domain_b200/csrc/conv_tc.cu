@@ -566,7 +566,7 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   if (split && block_n == 256) {
     // the 256-wide split tile stages its output through one slot while the same warps must keep draining the next tile's
     // chunk sums, which only amortises over a long K loop: measured 15.19k / 15.31k / 15.41k pairs/s for a threshold of
-    // 6 / 8 / 10 K blocks (profiles/r2_per_op_fp16x3_resnet50.txt)
+    // 6 / 8 / 10 K blocks (profiles/r2_x3_per_op.txt)
     static const int min_kb = getenv("SEMDIFF_X3_N256_MIN_KB") ? atoi(getenv("SEMDIFF_X3_N256_MIN_KB")) : 10;
     if (p.num_kb < min_kb) block_n = 128;
   }
