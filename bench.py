@@ -260,16 +260,17 @@ def copy_ceiling(ctx, host_tensors, steps: int):
 
 
 def e2e_run(ctx, model, g_h, s_h, outs_h, steps: int, pairs_total: int):
-    """`steps` calls of model.score_host with two in flight: step i+1's images cross PCIe while step i is scored; every
-    step's scores are read back to the host and waited for."""
+    """`steps` calls of model.score_host with three in flight (its staging ring has three slots): the images of steps i+1
+    and i+2 cross PCIe / are queued while step i is scored; every step's scores are read back to the host and waited for."""
     def loop(k):
-        pending = None
+        pending = []
         for i in range(k):
-            _, ev = model.score_host(g_h, s_h, outs_h[i % 2], wait=False)
-            if pending is not None:
-                pending.synchronize()
-            pending = ev
-        pending.synchronize()
+            _, ev = model.score_host(g_h, s_h, outs_h[i % len(outs_h)], wait=False)
+            pending.append(ev)
+            if len(pending) > 2:
+                pending.pop(0).synchronize()
+        for ev in pending:
+            ev.synchronize()
 
     loop(3)
     ms = ctx.timed(lambda: loop(steps), 1)
@@ -323,15 +324,15 @@ def run_pairs224(args, ctx):
     # ---- e2e: host buffers in, host scores out, through the public API -------------------------
     gt_h = torch.empty(n, 3, H, W, pin_memory=True).copy_(gt)
     sr_h = torch.empty(n, 3, H, W, pin_memory=True).copy_(sr)
-    outs_h = [torch.empty(n, pin_memory=True) for _ in range(2)]
+    outs_h = [torch.empty(n, pin_memory=True) for _ in range(3)]
     e2e_steps = max(4, args.steps // 2)
     e2e = e2e_run(ctx, model, gt_h, sr_h, outs_h, e2e_steps, total_pairs)
-    e2e["how"] = ("model.score_host(pinned fp32 gt, pinned fp32 sr) -> pinned scores, two steps in flight: the H2D copy of step i+1 "
-                  "(copy stream, 2 staging slots) overlaps the scoring of step i; `ceiling` = the same bytes copied with nothing else running")
+    e2e["how"] = ("model.score_host(pinned fp32 gt, pinned fp32 sr) -> pinned scores, three steps in flight: the H2D copies of steps i+1 / i+2 "
+                  "(copy stream, 3 staging slots) overlap the scoring of step i; `ceiling` = the same bytes copied with nothing else running")
     e2e["numa_binding"] = ctx.numa
     e2e["frac_of_device_value"] = e2e["value"] / value
     ref_scores = scores[rank * n:(rank + 1) * n].cpu() if world > 1 else scores.cpu()
-    assert torch.equal(outs_h[0], ref_scores) and torch.equal(outs_h[1], ref_scores), "e2e result differs"
+    assert all(torch.equal(o, ref_scores) for o in outs_h), "e2e result differs"
     # compact host inputs: what a data loader that keeps 16-bit tensors / decoded uint8 images hands over
     variants = {}
     if args.precision in ("bf16", "fp16"):

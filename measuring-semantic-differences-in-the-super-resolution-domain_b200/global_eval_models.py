@@ -287,11 +287,12 @@ class _B200Scorer(nn.Module):
         through `gpu_processor` (the reference's `model.processor`, bit-exact, on the device) after the copy - a quarter
         of the fp32 bytes at the same image size.
 
-        The images cross PCIe on a copy stream into a ring of two device staging slots while the previous slot is
+        The images cross PCIe on a copy stream into a ring of three device staging slots while earlier slots are
         being scored on the current stream, so the transfer overlaps the kernels - within one call when it spans
-        several chunks, and across calls when the caller keeps two calls in flight (`wait=False` returns
-        `(out_host, event)`; the scores are valid after `event.synchronize()`).  Chunking does not change any pair's
-        arithmetic."""
+        several chunks, and across calls when the caller keeps up to three calls in flight (`wait=False` returns
+        `(out_host, event)`; the scores are valid after `event.synchronize()`): the copy of call i+2 is then already
+        queued while call i is being scored, so host-side launch latency never sits between a copy and the kernels
+        that wait for it.  Chunking does not change any pair's arithmetic."""
         u8 = gt_host.dtype == torch.uint8
         if u8:
             n, H, W, _ = gt_host.shape
@@ -313,8 +314,8 @@ class _B200Scorer(nn.Module):
         if getattr(self, "_stage_shape", None) != key:
             torch.cuda.synchronize(dev)
             self._stage = [(torch.empty(chunk, *gt_host.shape[1:], device=dev, dtype=gt_host.dtype),
-                            torch.empty(chunk, *gt_host.shape[1:], device=dev, dtype=gt_host.dtype)) for _ in range(2)]
-            self._stage_consumed = [None, None]       # event: the scoring that last read this slot has finished
+                            torch.empty(chunk, *gt_host.shape[1:], device=dev, dtype=gt_host.dtype)) for _ in range(3)]
+            self._stage_consumed = [None, None, None]   # event: the scoring that last read this slot has finished
             self._stage_next = 0
             self._stage_shape = key
             self._copy_stream = torch.cuda.Stream(device=dev)
@@ -323,7 +324,7 @@ class _B200Scorer(nn.Module):
         for lo in range(0, n, chunk):
             hi = min(n, lo + chunk)
             slot = self._stage_next
-            self._stage_next ^= 1
+            self._stage_next = (slot + 1) % 3
             g_buf, s_buf = self._stage[slot]
             copied = torch.cuda.Event()
             with torch.cuda.stream(self._copy_stream):
