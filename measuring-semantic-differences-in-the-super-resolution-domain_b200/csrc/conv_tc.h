@@ -27,6 +27,7 @@ struct alignas(64) ConvTcParams {
   int has_src2;
   // split precisions (conv_tc_split.cu): stored tensors carry 2 x 64 columns (hi, lo) per k-block / 64 output channels
   int chunk_kb;                     // k-blocks accumulated in TMEM before the sum is promoted to registers
+  int stages, ring;                 // operand-ring fills / C-ring groups (split_ring_config)
   float acc_scale;                  // 1 / wscale, applied to the accumulator before the bias
 };
 static_assert(sizeof(ConvTcParams) <= 896, "ConvTcLaunch::params too small");
@@ -44,5 +45,6 @@ int num_sms();
 
 // split-precision launch (conv_tc_split.cu); p prepared by conv_tc_prepare
 int launch_conv_split(const ConvTcParams& p, int block_n, int a_mode, int precision, cudaStream_t st);
+void split_ring_config(int block_n, bool has_res, int* stages, int* ring);
 
 }  // namespace semdiff

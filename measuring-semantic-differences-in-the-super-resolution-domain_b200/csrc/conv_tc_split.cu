@@ -36,15 +36,19 @@ namespace semdiff {
 template <int BLOCK_N> struct SplitCfg {
   static constexpr int B_TILE_BYTES = BLOCK_N * BLOCK_K * 2;                      // one weight tile (hi or lo)
   static constexpr int STAGE_BYTES = 2 * A_STAGE_BYTES + 2 * B_TILE_BYTES;        // A hi | A lo | W hi | W lo
-  static constexpr int STAGES = BLOCK_N == 64 ? 3 : 2;
   static constexpr int GROUPS = BLOCK_N / 64;            // output groups: 64 accumulator columns = [64 hi | 64 lo] stored
   static constexpr int BOX_BYTES = BLOCK_M * 64 * 2;     // one 64-column 16-bit box of 128 rows
   static constexpr int GROUP_BYTES = 2 * BOX_BYTES;
-  static constexpr int RING = BLOCK_N == 256 ? 1 : (BLOCK_N == 128 ? 3 : 2);
+  // The operand ring (p.stages fills) and the C ring (p.ring output groups) share 224 KB; the host picks the split per conv
+  // (split_ring_config): a deep operand ring hides the TMA latency of the im2col / short-K tiles, a deep C ring keeps the
+  // residual prefetch of the HBM-bound residual convs ahead.
+  static constexpr int MAX_STAGES = BLOCK_N == 64 ? 4 : (BLOCK_N == 128 ? 3 : 2);
+  static constexpr int MAX_RING = 3;
+  static constexpr int DATA_BYTES = 224 * 1024;
   static constexpr int ACC_STAGES = BLOCK_N == 256 ? 2 : 4;   // chunk accumulators in flight: the MMA warp runs this far ahead of the drain
   static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;      // 256 / 512 / 512 columns
-  static constexpr int NUM_BARS = 2 * STAGES + 2 * ACC_STAGES + 2 * RING;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RING * GROUP_BYTES + NUM_BARS * 8 + 16 + 1024;
+  static constexpr int NUM_BARS = 2 * MAX_STAGES + 2 * ACC_STAGES + 2 * MAX_RING;
+  static constexpr int SMEM_BYTES = DATA_BYTES + NUM_BARS * 8 + 16 + 1024;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 };
 
@@ -53,17 +57,18 @@ constexpr int SPLIT_THREADS = 11 * 32;
 template <typename T, int BLOCK_N, int kAMode>
 __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = SplitCfg<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES, RING = Cfg::RING, GROUPS = Cfg::GROUPS, EPI_WARPS = 8, ACC = Cfg::ACC_STAGES;
+  constexpr int GROUPS = Cfg::GROUPS, EPI_WARPS = 8, ACC = Cfg::ACC_STAGES;
+  const int STAGES = p.stages, RING = p.ring;   // stages * STAGE_BYTES + ring * GROUP_BYTES <= DATA_BYTES (host-checked)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_c = smem + STAGES * Cfg::STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_c + RING * Cfg::GROUP_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::DATA_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::MAX_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::MAX_STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC;
   uint64_t* res_full_bar = tmem_empty_bar + ACC;
-  uint64_t* staged_bar = res_full_bar + RING;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(staged_bar + RING);
+  uint64_t* staged_bar = res_full_bar + Cfg::MAX_RING;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(staged_bar + Cfg::MAX_RING);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -306,6 +311,11 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const _
 template <typename T, int BLOCK_N, int kAMode>
 static int launch_split_t(const ConvTcParams& p, cudaStream_t st) {
   using Cfg = SplitCfg<BLOCK_N>;
+  if (p.stages < 2 || p.stages > Cfg::MAX_STAGES || p.ring < 1 || p.ring > Cfg::MAX_RING ||
+      p.stages * Cfg::STAGE_BYTES + p.ring * Cfg::GROUP_BYTES > Cfg::DATA_BYTES) {
+    set_error("conv_tc (split): bad ring configuration %d / %d for a %d-wide tile", p.stages, p.ring, BLOCK_N);
+    return SEMDIFF_ERR_ARG;
+  }
   static bool configured[MAX_DEVICES] = {};
   auto kern = conv_tc_split_kernel<T, BLOCK_N, kAMode>;
   const int dev = current_device();
@@ -336,6 +346,17 @@ static int launch_split_n(const ConvTcParams& p, int block_n, int a_mode, cudaSt
   }
   set_error("conv_tc (split): unsupported tile %d / mode %d", block_n, a_mode);
   return SEMDIFF_ERR_UNSUPPORTED;
+}
+
+// operand-ring fills and C-ring groups of a split conv (224 KB in total): 64-wide tiles 4 + 1 or 3 + 2, 128-wide 3 + 1 or
+// 2 + 3, 256-wide 2 + 1.  Residual convs keep the deep C ring (their residual tiles are prefetched RING - 1 groups ahead and
+// they are HBM-bound), everything else the deep operand ring.  SEMDIFF_X3_DEEP_RING=0 restores the shallow operand ring.
+void split_ring_config(int block_n, bool has_res, int* stages, int* ring) {
+  static const bool deep = getenv("SEMDIFF_X3_DEEP_RING") == nullptr || atoi(getenv("SEMDIFF_X3_DEEP_RING")) != 0;
+  const bool d = deep && !has_res;
+  if (block_n == 64) { *stages = d ? 4 : 3; *ring = d ? 1 : 2; }
+  else if (block_n == 128) { *stages = d ? 3 : 2; *ring = d ? 1 : 3; }
+  else { *stages = 2; *ring = 1; }
 }
 
 int launch_conv_split(const ConvTcParams& p, int block_n, int a_mode, int precision, cudaStream_t st) {
