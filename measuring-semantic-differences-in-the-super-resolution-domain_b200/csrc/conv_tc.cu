@@ -579,7 +579,7 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
   // chunk length of the promoted accumulation in k-blocks; SEMDIFF_X3_CHUNK_KB overrides (A/B testing)
   static const int chunk_kb = getenv("SEMDIFF_X3_CHUNK_KB") ? atoi(getenv("SEMDIFF_X3_CHUNK_KB")) : 1;
   p.chunk_kb = chunk_kb < 1 ? 1 : chunk_kb;
-  if (split) split_ring_config(block_n, res != nullptr, &p.stages, &p.ring);
+  if (split) split_ring_config(block_n, res != nullptr, p.num_kb, &p.stages, &p.ring);
   p.cpt = s.cin / 8;
   p.taps = s.kh * s.kw;
   const uint32_t box_cols = block_n < 64 ? block_n : 64;

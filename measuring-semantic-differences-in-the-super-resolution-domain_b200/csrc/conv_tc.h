@@ -45,6 +45,6 @@ int num_sms();
 
 // split-precision launch (conv_tc_split.cu); p prepared by conv_tc_prepare
 int launch_conv_split(const ConvTcParams& p, int block_n, int a_mode, int precision, cudaStream_t st);
-void split_ring_config(int block_n, bool has_res, int* stages, int* ring);
+void split_ring_config(int block_n, bool has_res, int num_kb, int* stages, int* ring);
 
 }  // namespace semdiff

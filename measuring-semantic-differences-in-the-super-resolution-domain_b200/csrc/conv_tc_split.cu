@@ -349,11 +349,13 @@ static int launch_split_n(const ConvTcParams& p, int block_n, int a_mode, cudaSt
 }
 
 // operand-ring fills and C-ring groups of a split conv (224 KB in total): 64-wide tiles 4 + 1 or 3 + 2, 128-wide 3 + 1 or
-// 2 + 3, 256-wide 2 + 1.  Residual convs keep the deep C ring (their residual tiles are prefetched RING - 1 groups ahead and
-// they are HBM-bound), everything else the deep operand ring.  SEMDIFF_X3_DEEP_RING=0 restores the shallow operand ring.
-void split_ring_config(int block_n, bool has_res, int* stages, int* ring) {
+// 2 + 3, 256-wide 2 + 1.  A deep operand ring hides the TMA latency of long K loops (measured, profiles/r2_x3_ring_ab.txt:
+// 3x3 convs -3..4 %, 512 -> 128 -10 %); short K loops (< 8 K blocks) are store-bound and residual convs prefetch their
+// residual tiles RING - 1 groups ahead, so both keep the deep C ring (64 -> 256 with one slot: +50 %).
+// SEMDIFF_X3_DEEP_RING=0 restores the shallow operand ring everywhere.
+void split_ring_config(int block_n, bool has_res, int num_kb, int* stages, int* ring) {
   static const bool deep = getenv("SEMDIFF_X3_DEEP_RING") == nullptr || atoi(getenv("SEMDIFF_X3_DEEP_RING")) != 0;
-  const bool d = deep && !has_res;
+  const bool d = deep && !has_res && num_kb >= 8;
   if (block_n == 64) { *stages = d ? 4 : 3; *ring = d ? 1 : 2; }
   else if (block_n == 128) { *stages = d ? 3 : 2; *ring = d ? 1 : 3; }
   else { *stages = 2; *ring = 1; }
