@@ -76,6 +76,21 @@ def test_fp16x3_mode_matches_oracle(trunk):
     assert e < 1e-5, (got, ref)
 
 
+def test_bf16x3_mode_within_north_star_tolerance():
+    """The same split kernels with bf16 halves (16 significant bits, fp32 exponent range: no saturation risk on trunks whose
+    activations exceed fp16's 65504): inside the 1e-3 the north_star asks of the tensor-core trunk, incl. SR ~ GT pairs."""
+    oracle, model = oracle_and_module("resnet50", 3, "bf16x3")
+    gt, sr = make_pairs(8, seed=0)
+    gt2, sr2 = make_pairs(8, seed=43, sigma_lo=0.02, sigma_hi=0.03)
+    gt, sr = torch.cat([gt, gt2]), torch.cat([sr, sr2])
+    ref = oracle(gt, sr)
+    with torch.no_grad():
+        got = model(gt.cuda(), sr.cuda()).cpu()
+    e = rel_err(got, ref)
+    print(f"[parity] resnet50 bf16x3 max rel err vs oracle fp32 {e:.3g} (low-sigma half {rel_err(got[8:], ref[8:]):.3g})")
+    assert e < 1e-3, (got, ref)
+
+
 def test_fp16x3_low_sigma_and_sweep_distribution():
     """>= 128 pairs of the sweep distribution (sigma log-uniform in [0.02, 2]) plus 32 pairs forced into the SR ~ GT corner
     (sigma in [0.02, 0.03]) where 16-bit trunks lose the difference in their rounding: fp16x3 must hold the north_star
