@@ -428,6 +428,30 @@ def test_fp16x3_invariances():
         model(gt[:, :, :223], sr[:, :, :223])
 
 
+def test_split_kernels_are_repeatable_under_load():
+    """compute-sanitizer is closed on this pool, so races in the mbarrier / TMEM protocols of the split kernel (four TMEM
+    stages, chunk sums drained while the next chunks accumulate, runtime ring split) have to show up as non-determinism:
+    300 pairs (ragged micro-batches, many tiles per CTA) scored ten times, interleaved with another plan's kernels on the
+    same stream and with a second stream hammering HBM, must give bit-identical scores every time."""
+    oracle, mx = oracle_and_module("resnet50", 3, "fp16x3")
+    _, mb = oracle_and_module("resnet50", 3, "bf16")
+    g = torch.Generator(device="cuda").manual_seed(17)
+    gt = torch.randn(300, 3, 224, 224, device="cuda", generator=g)
+    sr = gt + 0.05 * torch.randn(300, 3, 224, 224, device="cuda", generator=g)
+    noise, side = torch.empty(64 << 20, device="cuda"), torch.cuda.Stream()
+    with torch.no_grad():
+        mx.microbatch = 128          # 128 + 128 + 44
+        first = mx(gt, sr)
+        for rep in range(10):
+            with torch.cuda.stream(side):
+                noise.normal_()
+            mb(gt[:32], sr[:32])
+            mx.microbatch = (128, 77, 300)[rep % 3]
+            assert torch.equal(mx(gt, sr), first), rep
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(first).all()) and float(first.std()) > 0
+
+
 def test_normalize_has_no_gradient_path():
     """the LPIPS-style normalised variant must not hand back gradients of the un-normalised function."""
     model = CLS["resnet50"]("resnet50", 0, "cuda", precision="bf16", normalize=True)
