@@ -571,7 +571,7 @@ int conv_tc_prepare(ConvTcLaunch* L, const ConvPtrs& q, const ConvShape& s, int 
     if (p.num_kb < min_kb) block_n = 128;
   }
   if (block_n == 0) { set_error("conv_tc: cout %d not a multiple of 32", s.cout); return SEMDIFF_ERR_UNSUPPORTED; }
-  p.in = in; p.out = out; p.bias = bias; p.has_res = res != nullptr;
+  p.in = in; p.bias = bias; p.has_res = res != nullptr;
   p.H = s.H; p.W = s.W; p.Cin = s.cin; p.OH = s.OH(); p.OW = s.OW(); p.Cout = s.cout;
   p.KH = s.kh; p.KW = s.kw; p.stride = s.stride; p.pad = s.pad; p.relu = s.relu;
   p.n_tiles = s.cout / block_n;

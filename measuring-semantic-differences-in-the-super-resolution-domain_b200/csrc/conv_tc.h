@@ -20,7 +20,6 @@ struct alignas(64) ConvTcParams {
   CUtensorMap tmC;  // output as [M, Cout]
   CUtensorMap tmR;  // residual as [M, Cout]
   const void* in;
-  void* out;        // split kernel, 256-wide tiles: direct stores
   const float* bias;
   int H, W, Cin, OH, OW, Cout, KH, KW, stride, pad, relu, has_res;
   int M, num_kb, m_tiles, n_tiles, cpt, taps;

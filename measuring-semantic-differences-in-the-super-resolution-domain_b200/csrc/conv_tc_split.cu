@@ -26,7 +26,6 @@
 //              of its half; it sums the chunk accumulators in registers, then + bias (+ residual) -> ReLU -> split into
 //              hi / lo -> the group's two swizzled 64-column boxes
 //   warp 10    C-ring I/O: TMA store of staged groups, slot grants + residual (hi and lo box) prefetch
-//              (256-wide tiles: none of it - their epilogue writes 64-byte runs straight to global memory)
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -59,7 +58,6 @@ template <typename T, int BLOCK_N, int kAMode>
 __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const __grid_constant__ ConvTcParams p) {
   using Cfg = SplitCfg<BLOCK_N>;
   constexpr int GROUPS = Cfg::GROUPS, EPI_WARPS = 8, ACC = Cfg::ACC_STAGES;
-  constexpr bool kDirect = BLOCK_N == 256;   // the epilogue stores straight to global memory (no C ring, no I/O warp work)
   const int STAGES = p.stages, RING = p.ring;   // stages * STAGE_BYTES + ring * GROUP_BYTES <= DATA_BYTES (host-checked)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -217,40 +215,6 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const _
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       }
-      if constexpr (kDirect) {
-        // 256-wide tiles (never a residual): straight from the promoted registers to global memory.  A thread owns 32
-        // consecutive channels of one row per group = one 64-byte run of hi values and one of lo values: whole 32-byte
-        // sectors, no staging slot to wait for - the warps are back at the next tile's chunk sums right away (through one
-        // C slot the four groups of a tile serialise behind their TMA stores and the MMA warp runs out of TMEM stages).
-        const int gm = m_tile * BLOCK_M + row;
-        if (gm < p.M) {
-          T* orow = reinterpret_cast<T*>(p.out) + (int64_t)gm * (2 * p.Cout);
-#pragma unroll
-          for (int g = 0; g < GROUPS; ++g) {
-            const int col0 = n_tile * BLOCK_N + g * 64 + half * 32;
-            T* dst = orow + 2 * (n_tile * BLOCK_N + g * 64) + half * 32;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8));
-              const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j * 8 + 4));
-              float f[8] = {fmaf(racc[g][j * 8 + 0], sc, b0.x), fmaf(racc[g][j * 8 + 1], sc, b0.y), fmaf(racc[g][j * 8 + 2], sc, b0.z),
-                            fmaf(racc[g][j * 8 + 3], sc, b0.w), fmaf(racc[g][j * 8 + 4], sc, b1.x), fmaf(racc[g][j * 8 + 5], sc, b1.y),
-                            fmaf(racc[g][j * 8 + 6], sc, b1.z), fmaf(racc[g][j * 8 + 7], sc, b1.w)};
-              if (p.relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-              }
-              const uint4 oh = pack8<T>(f);
-              float h[8];
-              unpack8<T>(oh, h);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) h[e] = f[e] - h[e];
-              *reinterpret_cast<uint4*>(dst + j * 8) = oh;
-              *reinterpret_cast<uint4*>(dst + 64 + j * 8) = pack8<T>(h);
-            }
-          }
-        }
-      } else {
 #pragma unroll
       for (int g = 0; g < GROUPS; ++g) {
         uint8_t* cbuf = smem_c + slot * Cfg::GROUP_BYTES;
@@ -294,11 +258,10 @@ __global__ void __launch_bounds__(SPLIT_THREADS, 1) conv_tc_split_kernel(const _
         if (lane == 0) mbar_arrive(&staged_bar[slot]);
         if (++slot == RING) { slot = 0; sphase ^= 1; }
       }
-      }
     }
   } else {
     // ===================== C-ring I/O: TMA stores of staged groups + slot grants / residual prefetch =====================
-    if (!kDirect && leader && blockIdx.x < total_tiles) {
+    if (leader && blockIdx.x < total_tiles) {
       pdl_wait();
       const int total = GROUPS * ((total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x);
       int k_load = 0, l_slot = 0, l_g = 0, l_tile = blockIdx.x;
