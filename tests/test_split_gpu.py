@@ -51,6 +51,32 @@ def test_conv_split(case, precision):
     assert out.shape == ref.shape and err < TOL[precision]
 
 
+def test_conv_split_random_shapes():
+    """Seeded random geometries (odd sizes, strides, 1x1 / 3x3 / 5x5 windows, channel counts that are not powers of two,
+    residual on / off): every combination of tile width, A mode and ring configuration the host can pick."""
+    import random
+    rng = random.Random(1234)
+    for trial in range(16):
+        k = rng.choice([1, 1, 3, 3, 5])
+        stride = rng.choice([1, 1, 2])
+        cin, cout = rng.choice([64, 128, 192, 320]), rng.choice([64, 128, 192, 256, 512])
+        n, H, W = rng.randint(1, 5), rng.randint(k + 2, 33), rng.randint(k + 2, 33)
+        with_res = rng.random() < 0.4
+        pad = k // 2
+        g = torch.Generator(device=DEV).manual_seed(100 + trial)
+        x = split_store(torch.randn(n, H, W, cin, device=DEV, generator=g), torch.float16)
+        w = split_store(torch.randn(cout, k, k, cin, device=DEV, generator=g) * (2.0 / (k * k * cin)) ** 0.5, torch.float16)
+        b = torch.randn(cout, device=DEV, generator=g) * 0.1
+        oh, ow = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        res = split_store(torch.randn(n, oh, ow, cout, device=DEV, generator=g), torch.float16) if with_res else None
+        out = split_value(conv2d(x, w, b, res, stride, pad, True, "fp16x3", _lib.CONV_TC_TMA))
+        ref = torch.nn.functional.conv2d(split_value(x).permute(0, 3, 1, 2), split_value(w).permute(0, 3, 1, 2), b.double(),
+                                         stride=stride, padding=pad).permute(0, 2, 3, 1)
+        ref = torch.relu(ref + split_value(res)) if with_res else torch.relu(ref)
+        err = ((out - ref).abs().max() / ref.abs().max()).item()
+        assert err < TOL["fp16x3"], (trial, n, H, W, cin, cout, k, stride, with_res, err)
+
+
 @pytest.mark.parametrize("precision", ["fp16x3", "bf16x3"])
 def test_conv_split_second_source(precision):
     """Projection shortcut folded into conv3's launch: K blocks of a second, strided activation tensor."""
