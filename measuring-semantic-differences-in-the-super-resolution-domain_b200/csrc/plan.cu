@@ -21,12 +21,17 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// Measured on B200 (profiles/r1_pdl.txt): programmatic dependent launch changes the step time by -1 % (RN50 6.18 -> 6.25 ms,
-// CLIP 8.40 -> 8.53 ms) - the persistent kernels all end within a tile of each other and the plain launch gap is ~1 us -
-// so it is off unless SEMDIFF_PDL=1.
+// Programmatic dependent launch (every kernel starts with pdl_trigger / guards its first dependent access with pdl_wait):
+// the next kernel's prologue - barrier init, TMEM allocation, descriptor prefetch, resident weights - overlaps the tail of the
+// previous one.  Measured on B200: at 256 pairs per pass it changes nothing (-1 %: the persistent kernels all end within a
+// tile of each other, profiles/r1_pdl.txt), but small passes are chains of ~10 us kernels whose prologues are a third of
+// their run time: 5 pairs 0.617 -> 0.516 ms (bf16), 1.10 -> 1.00 ms (fp16x3); 32 pairs 1.12 -> 1.02 ms (profiles/r2_pdl_small_batch.txt).
+// So the executor turns it on per pass when the pass is small (<= 10 M input pixels ~ 100 pairs of 224x224).
+// SEMDIFF_PDL=1 / =0 forces it on / off.
+static thread_local bool g_pdl_auto = false;
 bool pdl_enabled() {
-  static const bool on = getenv("SEMDIFF_PDL") != nullptr;
-  return on;
+  static const int forced = getenv("SEMDIFF_PDL") == nullptr ? -1 : (atoi(getenv("SEMDIFF_PDL")) != 0 || getenv("SEMDIFF_PDL")[0] == '\0' ? 1 : 0);
+  return forced >= 0 ? forced != 0 : g_pdl_auto;
 }
 
 struct BufShape { int h = 0, w = 0, c = 0, pp = 2; };   // pp: images per pair held by the buffer (1 downstream of SQDIFF)
@@ -439,6 +444,7 @@ static int run_program(semdiff_plan* P, const void* gt, const void* sr, int32_t 
 
   for (int p0 = 0; p0 < n_pairs; p0 += mb) {
     const int cur = n_pairs - p0 < mb ? n_pairs - p0 : mb;
+    g_pdl_auto = 2ll * cur * H * W <= 10000000ll;   // small pass: overlap every kernel's prologue with its predecessor's tail
     ShapePlan& S = P->shapes[std::make_tuple(cur, H, W)];
     if (S.total_bytes == 0) {
       int rc = infer_shapes(P, cur, H, W, &S);
@@ -540,6 +546,7 @@ static int run_program(semdiff_plan* P, const void* gt, const void* sr, int32_t 
       P->last_launches++;
     }
   }
+  g_pdl_auto = false;
   return 0;
 }
 
