@@ -26,7 +26,7 @@ void set_error(const char* fmt, ...) {
 // previous one.  Measured on B200: at 256 pairs per pass it changes nothing (-1 %: the persistent kernels all end within a
 // tile of each other, profiles/r1_pdl.txt), but small passes are chains of ~10 us kernels whose prologues are a third of
 // their run time: 5 pairs 0.617 -> 0.516 ms (bf16), 1.10 -> 1.00 ms (fp16x3); 32 pairs 1.12 -> 1.02 ms (profiles/r2_pdl_small_batch.txt).
-// So the executor turns it on per pass when the pass is small (<= 10 M input pixels ~ 100 pairs of 224x224).
+// So the executor turns it on per pass when the pass is small (<= 8 M input pixels ~ 80 pairs of 224x224; split precisions 2 M).
 // SEMDIFF_PDL=1 / =0 forces it on / off.
 static thread_local bool g_pdl_auto = false;
 bool pdl_enabled() {
@@ -444,7 +444,9 @@ static int run_program(semdiff_plan* P, const void* gt, const void* sr, int32_t 
 
   for (int p0 = 0; p0 < n_pairs; p0 += mb) {
     const int cur = n_pairs - p0 < mb ? n_pairs - p0 : mb;
-    g_pdl_auto = 2ll * cur * H * W <= 10000000ll;   // small pass: overlap every kernel's prologue with its predecessor's tail
+    // small pass: overlap every kernel's prologue with its predecessor's tail (the split kernels' longer main loops amortise
+    // their prologue sooner: 4 pairs of 1024x1024 in fp16x3 are 3.6 % SLOWER with it)
+    g_pdl_auto = 2ll * cur * H * W <= (is_split(P->precision) ? 2000000ll : 8000000ll);
     ShapePlan& S = P->shapes[std::make_tuple(cur, H, W)];
     if (S.total_bytes == 0) {
       int rc = infer_shapes(P, cur, H, W, &S);
