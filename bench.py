@@ -365,12 +365,26 @@ def run_pairs224(args, ctx):
         x3_steps = max(4, args.steps // 2)
         msx = ctx.timed(stepx, x3_steps)
         ex = e2e_run(ctx, mx, gt_h, sr_h, outs_h, max(4, x3_steps // 2), total_pairs)
+        px = mx.plan()
+        px.set_profiling(True)
+        stepx()
+        px.profile(reset=True)
+        for _ in range(2):
+            stepx()
+        x_ms, _ = px.profile(reset=True)
+        px.set_profiling(False)
+        x_conv_ms = sum(x_ms[i] for i, op in enumerate(px.program.ops) if op["kind"] == 0) / 2
+        x_alg = trunks.conv_flops(px.program, H, W) * 2 * n / (x_conv_ms / 1e3) / 1e12
         sx_local = sx[rank * n:(rank + 1) * n] if world > 1 else sx
         dev_rel = ((scores[rank * n:(rank + 1) * n] if world > 1 else scores) - sx_local).abs() / sx_local.abs().clamp_min(1e-3)
         x3 = {"precision": "fp16x3", "value": total_pairs * x3_steps / (msx / 1e3), "unit": UNIT, "ms_per_step": msx / x3_steps,
               "steps": x3_steps, "e2e": ex, "gpu_launches_per_step": mx.plan().last_launches(),
               "what": "every activation / weight = hi + lo fp16 pair, three tcgen05 products per K block, chunk sums promoted to "
                       "registers; <= 1e-5 of the fp32 oracle (tests/test_scorer_gpu.py)",
+              "roofline": {"bound": "tensor", "achieved": x_alg, "unit": "TFLOP/s of algorithmic work (conv launches, per-op CUDA events)",
+                           "tensor_core_tflops": 3 * x_alg, "frac_of_sustained_peak": 3 * x_alg / peaks["bf16_sustained"],
+                           "frac_of_burst_peak": 3 * x_alg / peaks["bf16_burst"],
+                           "note": "three fp16 tensor-core products per algorithmic multiply-add; 4-byte activations make the 56x56 / 28x28 1x1 layers HBM-bound"},
               "headline_mode_vs_this_mode_max_rel_diff": float(dev_rel.max())}
         del mx
 
