@@ -450,7 +450,37 @@ def run_pairs224(args, ctx):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_throughput(args.cpu_budget)
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line if args.detail else compact_line(line)), flush=True)
+
+
+def compact_line(line: dict) -> dict:
+    """The contract's keys with their numbers and short labels (< 3 KB on one line, so that a log tail always holds it whole);
+    `--detail` prints every note and sub-measurement instead (that is what the records under profiles/ are)."""
+    def pick(d, keys):
+        return {k: d[k] for k in keys if k in d}
+    out = pick(line, ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                      "dtype", "data", "gpu_launches", "clocks"))
+    out["config"] = pick(line["config"], ("workload", "pairs_per_gpu", "microbatch_pairs", "precision", "collective"))
+    out["config"]["l2"] = "inputs larger than L2, no flush needed"
+    e = line["e2e"]
+    out["e2e"] = pick(e, ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "steps", "ms_per_step", "frac_of_device_value"))
+    out["e2e"]["ceiling"] = pick(e["ceiling"], ("value", "h2d_gbs_per_gpu", "frac"))
+    out["e2e"]["variants"] = {k: pick(v, ("value", "h2d_bytes_per_step")) for k, v in e.get("variants", {}).items()}
+    r = line["roofline"]
+    out["roofline"] = pick(r, ("bound", "achieved", "peak", "unit", "frac", "frac_of_burst_peak", "frac_of_sustained_peak", "traffic",
+                               "launches_per_step", "avg_launch_ms", "share_of_step"))
+    out["roofline"]["kernel"] = "conv_tc + conv3x3_strip + conv_chain (tcgen05 implicit-GEMM convs of the trunk)"
+    out["roofline"]["peak_source"] = "MEASURED_PEAKS.json" if "measured" in r["peak_source"] else "fallback"
+    out["roofline_distance"] = pick(line["roofline_distance"], ("bound", "achieved", "peak", "unit", "frac"))
+    if "fp16x3" in line:
+        x = line["fp16x3"]
+        out["fp16x3"] = pick(x, ("value", "unit", "ms_per_step", "steps"))
+        out["fp16x3"]["e2e"] = pick(x["e2e"], ("value", "h2d_bytes_per_step", "d2h_bytes_per_step"))
+        out["fp16x3"].update(pick(x.get("roofline", {}), ("tensor_core_tflops", "frac_of_sustained_peak")))
+    if "cpu_baseline" in line:
+        out["cpu_baseline"] = pick(line["cpu_baseline"], ("value", "unit", "cores", "kind"))
+        out["cpu_baseline"]["sample"] = line["cpu_baseline"]["sample"][:90]
+    return out
 
 
 def distance_isolated(model, peaks):
@@ -712,6 +742,7 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-x3", action="store_true", help="skip the fp16x3 extra key")
+    ap.add_argument("--detail", action="store_true", help="pairs224: print every note and sub-measurement instead of the compact line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 

@@ -60,3 +60,20 @@ def test_kernel_source_stamp():
         tj = json.load(f)
     assert set(tj) >= {"kernel_sources_sha256", "conv_tc_dram_bytes_per_launch", "source"}
     assert os.path.isfile(os.path.join(ROOT, tj["source"]))
+
+
+def test_compact_line_keeps_the_contract_keys_and_stays_short():
+    """bench.py prints the compact form by default: every key of the contract, numbers only, short enough that a log tail holds
+    the whole line (the detailed records under profiles/ come from --detail)."""
+    with open(os.path.join(ROOT, "profiles", "r2_bench_1gpu.json")) as f:
+        detail = json.load(f)
+    c = bench.compact_line(detail)
+    line = json.dumps(c)
+    assert len(line) < 3000 and "\n" not in line
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in c, k
+    assert set(c["roofline"]) >= {"bound", "achieved", "peak", "unit", "frac", "traffic"}
+    assert set(c["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} and c["e2e"]["h2d_bytes_per_step"] > 0
+    assert set(c["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"}
+    assert "workload" in c["config"] and c["value"] == detail["value"] and c["fp16x3"]["value"] == detail["fp16x3"]["value"]

@@ -4,8 +4,8 @@
 mkdir -p gpurun_out
 timeout -s KILL 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3 | tee gpurun_out/r2_final_tests.log
 timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | grep -v Warn | tail -5 | tee gpurun_out/r2_final_smoke.log
-timeout -s KILL 600 python bench.py > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err; tail -2 gpurun_out/r2_final_bench.err
-timeout -s KILL 600 python bench.py --trunk resnet50_clip.openai --no-cpu-baseline > gpurun_out/r2_final_bench_clip.json 2>> gpurun_out/r2_final_bench.err
+timeout -s KILL 600 python bench.py --detail > gpurun_out/r2_final_bench.json 2> gpurun_out/r2_final_bench.err; tail -2 gpurun_out/r2_final_bench.err
+timeout -s KILL 600 python bench.py --detail --trunk resnet50_clip.openai --no-cpu-baseline > gpurun_out/r2_final_bench_clip.json 2>> gpurun_out/r2_final_bench.err
 timeout -s KILL 300 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/r2_final_bench_reference.json 2>> gpurun_out/r2_final_bench.err
 for prec in bf16 fp16x3; do for t in resnet50 resnet50_clip.openai; do
   timeout -s KILL 200 python tools/profile_ops.py --pairs 256 --microbatch 256 --precision $prec --trunk $t --steps 5 2>&1 | grep -v "Warn\|model = " > gpurun_out/r2_final_ops_${prec}_$t.txt
