@@ -75,13 +75,6 @@ struct semdiff_plan {
   std::vector<double> prof_ms;
   std::vector<int> prof_launches;
   int64_t last_launches = 0;
-  // Tap overlap: the distance kernel of a tapped activation is HBM-bound and nothing downstream of it on the trunk reads its
-  // result, so it runs on a side stream next to the (mostly tensor-bound) convs that follow; the trunk only waits for it
-  // before the first launch that overwrites the tapped buffer, and the head waits for all of them.
-  cudaStream_t side = nullptr;
-  int side_device = -1;
-  cudaEvent_t tap_ready[16] = {}, tap_done[16] = {};
-  int tap_pending_buf[16];   // buffer id a still-running distance launch reads, or -1
 };
 
 namespace semdiff {
@@ -385,11 +378,6 @@ int semdiff_plan_create(const semdiff_op* ops, int32_t n_ops, int32_t n_bufs, in
 int semdiff_plan_destroy(semdiff_plan* P) {
   if (P == nullptr) return 0;
   for (auto& e : P->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-  if (P->side != nullptr) {
-    cudaStreamSynchronize(P->side);
-    for (int j = 0; j < 16; ++j) { if (P->tap_ready[j]) cudaEventDestroy(P->tap_ready[j]); if (P->tap_done[j]) cudaEventDestroy(P->tap_done[j]); }
-    cudaStreamDestroy(P->side);
-  }
   delete P;
   return 0;
 }
@@ -474,34 +462,6 @@ static int run_program(semdiff_plan* P, const void* gt, const void* sr, int32_t 
     }
     float* partials = reinterpret_cast<float*>(ws + S.partial_offset);
     int tap_parts[16], tap_hw[16];
-    // distance launches next to the convs that follow them (see semdiff_plan::side): not while profiling per op, not in
-    // the small passes that chain their kernels with programmatic dependent launch; SEMDIFF_TAP_OVERLAP=0 disables it
-    static const bool overlap_ok = getenv("SEMDIFF_TAP_OVERLAP") == nullptr || atoi(getenv("SEMDIFF_TAP_OVERLAP")) != 0;
-    bool overlap = overlap_ok && !P->profiling && !P->has_map && !pdl_enabled();
-    if (overlap) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (P->side != nullptr && P->side_device != dev) overlap = false;   // a plan's side stream lives on the device it was first used on
-      if (overlap && P->side == nullptr) {
-        if (cudaStreamCreateWithFlags(&P->side, cudaStreamNonBlocking) != cudaSuccess) { P->side = nullptr; overlap = false; (void)cudaGetLastError(); }
-        else {
-          P->side_device = dev;
-          for (int j = 0; j < 16; ++j) {
-            cudaEventCreateWithFlags(&P->tap_ready[j], cudaEventDisableTiming);
-            cudaEventCreateWithFlags(&P->tap_done[j], cudaEventDisableTiming);
-          }
-        }
-      }
-    }
-    for (int j = 0; j < 16; ++j) P->tap_pending_buf[j] = -1;
-    // the trunk may not overwrite buffer `b` while a distance launch is still reading it
-    auto wait_for_readers = [&](int b) {
-      for (int j = 0; j < 16; ++j)
-        if (P->tap_pending_buf[j] >= 0 && (b < 0 || P->tap_pending_buf[j] == b)) {
-          cudaStreamWaitEvent(st, P->tap_done[j], 0);
-          P->tap_pending_buf[j] = -1;
-        }
-    };
     const int n_img = 2 * cur;
     const int64_t in_bytes = (int64_t)elem_bytes(in_precision);
     const char* gt_mb = reinterpret_cast<const char*>(gt) + p0 * img_elems * in_bytes;
@@ -519,27 +479,12 @@ static int run_program(semdiff_plan* P, const void* gt, const void* sr, int32_t 
         tap_parts[j] = distance_parts(hw, in.c);
         tap_hw[j] = hw;
         float* cm = out_chan_mean ? out_chan_mean + (int64_t)p0 * P->chan_total + P->tap_off[j] : nullptr;
-        cudaStream_t dst_stream = st;
-        if (overlap) {
-          cudaEventRecord(P->tap_ready[j], st);
-          cudaStreamWaitEvent(P->side, P->tap_ready[j], 0);
-          dst_stream = P->side;
-        }
         rc = launch_distance(src, cur, hw, in.c, head_w + P->tap_off[j], normalize,
-                             partials + (int64_t)j * cur * SEMDIFF_MAX_PARTS, cm, P->chan_total, P->precision, dst_stream);
-        if (overlap) {
-          cudaEventRecord(P->tap_done[j], P->side);
-          P->tap_pending_buf[j] = op.src;
-        }
+                             partials + (int64_t)j * cur * SEMDIFF_MAX_PARTS, cm, P->chan_total, P->precision, st);
         P->last_launches += cm ? 2 : 1;
         return rc;
       }
       ProfScope ps(P, i, st);
-      if (overlap) {   // every buffer this launch writes: its own destination and those of the ops fused into it
-        wait_for_readers(op.dst);
-        for (int k = i + 1; k < n_ops && (S.fused_away[k] || P->ops[k].kind == SEMDIFF_OP_TAP); ++k)
-          if (S.fused_away[k]) wait_for_readers(P->ops[k].dst);
-      }
       if (op.kind == SEMDIFF_OP_MAP_OUT) {
         P->last_launches++;
         return launch_decoder_op(3, src, nullptr, out_map + (int64_t)p0 * S.map_h * S.map_w, cur, in.h, in.w, in.c, 0, P->precision, st);
@@ -595,7 +540,6 @@ static int run_program(semdiff_plan* P, const void* gt, const void* sr, int32_t 
       int rc = run_op(i, n_img, 0, false);
       if (rc != 0) return rc;
     }
-    wait_for_readers(-1);   // the head reads every tap's partial sums
     if (!P->has_map) {
       ProfScope ps(P, n_ops + 2, st);
       int rc = launch_head(partials, P->n_taps, cur, tap_parts, tap_hw, head_b, out_scores + p0,
