@@ -32,7 +32,8 @@ enum { SEMDIFF_OK = 0, SEMDIFF_ERR_ARG = -1, SEMDIFF_ERR_CUDA = -2, SEMDIFF_ERR_
 /* storage/compute type of the trunk.  Accumulation is always fp32.
  * The two "x3" types are SPLIT types: every activation and weight is the unevaluated sum hi + lo of two 16-bit numbers
  * (hi = round(x), lo = round(x - hi): 22 significant bits for fp16, 16 for bf16), and every conv runs as three tensor-core
- * products per K block, Ah*Wh + Al*Wh + Ah*Wl, into one fp32 accumulator (the Al*Wl term is below fp32 resolution).
+ * products per K block, Al*Wh + Ah*Wl + Ah*Wh (small terms first; the Al*Wl term is below fp32 resolution), whose chunk sums
+ * are added in registers with round-to-nearest because the tensor core truncates its fp32 accumulator (csrc/conv_tc_split.cu).
  * Split activations are stored NHWC with 2*C 16-bit channels: for each block of 64 logical channels, 64 hi values then
  * 64 lo values.  Split conv weights are [Cout][2*K] with the same interleave along K, pre-multiplied by the power of two
  * semdiff_op.wscale (keeps the lo halves in the normal fp16 range); the epilogue multiplies the accumulator by 1/wscale. */
@@ -63,7 +64,7 @@ enum {
   /* local-map decoder (/root/reference/models/local_eval_models.py:109-125): buffers written by SQDIFF hold ONE image per
    * pair (everything downstream of it too); all other buffers hold two (GT image, SR image) */
   SEMDIFF_OP_SQDIFF = 4,     /* dst[pair] = (src[GT image] - src[SR image])^2                      (:115) */
-  SEMDIFF_OP_CONCAT = 5,     /* dst = channel concat (src | src2); cin / cin2 = their channel counts (:121) */
+  SEMDIFF_OP_CONCAT = 5,     /* dst = channel concat (src | src2); channel counts come from the buffers (:121) */
   SEMDIFF_OP_UPSAMPLE2X = 6, /* nn.UpsamplingBilinear2d(scale_factor=2): bilinear, align_corners   (:84, :119, :123) */
   SEMDIFF_OP_MAP_OUT = 7     /* channel 0 of src -> bilinear x2 -> sigmoid -> the fp32 output map   (:123-125) */
 };
