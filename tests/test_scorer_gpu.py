@@ -341,7 +341,7 @@ def test_wperlay_variant(depth):
     oracle = set_head(RestatedScorer("resnet50_clip.openai", depth, seed=0, variant="wperlay"), "abs")
     gt, sr = make_pairs(3, seed=17)
     ref = oracle(gt, sr)
-    for precision, tol in (("fp32", 1e-5), ("bf16", 6e-2)):
+    for precision, tol in (("fp32", 1e-5), ("fp16x3", 1e-5), ("bf16", 6e-2)):
         model = semdiff_b200.CLIP_lpips_wperlay_cnn("resnet50_clip.openai", depth, "cuda", precision=precision)
         assert model.wanted_layers == oracle.wanted_layers
         model.load_state_dict(oracle.state_dict(), strict=True)
